@@ -1,0 +1,36 @@
+"""Shared helpers for the tests: re-create golden inputs from seeds, call the oracle."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from quantization_b200 import synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_case_names():
+    g = np.load(os.path.join(GOLDEN_DIR, "golden_cases.npz"))
+    return list(json.loads(bytes(g["meta_json"]).decode()).keys())
+
+
+def case_inputs(m):
+    """(x in its stored dtype, params dict) for a golden case; verifies the SHA-256 stored with the fixture."""
+    p = synth.synth_params(m["D"], m["N"], m["K"], m["seed_p"])
+    x = synth.synth_x(m["B"], m["D"], m["seed_x"], getattr(torch, m["x_dtype"]))
+    assert synth.sha256_of(x) == m["sha_x"], "synthetic frames drifted from the fixture"
+    assert synth.sha256_of(p["centers"], p["weight"], p["bias"]) == m["sha_params"], "synthetic params drifted"
+    return x, p
+
+
+def trained_params(gt, tag):
+    """Parameters of the reference-trained quantizer stored in golden_trained.npz (tag 'p1' or 'p2')."""
+    return dict(
+        centers=torch.from_numpy(gt[f"{tag}/centers"]),
+        weight=torch.from_numpy(gt[f"{tag}/to_logits.weight"]),
+        bias=torch.from_numpy(gt[f"{tag}/to_logits.bias"]),
+        centers_scale=float(gt[f"{tag}/centers_scale"]),
+        logits_scale=float(gt[f"{tag}/logits_scale"]),
+        id_buf=torch.from_numpy(gt[f"{tag}/id_buf"]),
+    )
