@@ -1,0 +1,136 @@
+/*
+ * mcq.h -- C ABI of libmcq.so: B200 (sm_100a) kernels for the additive multi-codebook
+ * encode / refine / decode hot path of danpovey/quantization.
+ *
+ * The reference is pure Python/PyTorch and has no FFI layer; its "operator interface" for
+ * this path is the body of four Python methods (paths relative to
+ * /root/reference/quantization/quantization.py):
+ *
+ *   mcq_prepare          <- Quantizer.get_centers (:77-79), the exp() scale of Quantizer._logits (:278),
+ *                           all_centers_sumsq (:411); run once per parameter version
+ *   mcq_encode           <- Quantizer.encode (:244-275) = _compute_indexes (:281-305) + byte packing (:266-272)
+ *   mcq_refine           <- `iters` x Quantizer._refine_indexes (:308-547) from caller-supplied indexes
+ *                           (what compute_loss / QuantizerTrainer.step reach, :212, :652)
+ *   mcq_decode           <- Quantizer.decode (:117-148) incl. _maybe_separate_indexes (:551-573)
+ *   mcq_decode_backward  <- autograd of decode w.r.t. the scaled centers (used by compute_loss, :213-216)
+ *   mcq_encode_host      <- the same encode for a caller that holds HOST buffers (what a cgo/JNI/ctypes
+ *                           host without its own CUDA plumbing binds)
+ *
+ * Conventions: plain pointers and sizes only.  Every function returns 0 on success or a negative
+ * MCQ_E* code; mcq_last_error() gives the thread's last message.  Unless the name ends in _host,
+ * all data pointers are DEVICE pointers, nothing is allocated or freed, nothing synchronises: all
+ * work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ */
+#ifndef MCQ_H_
+#define MCQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCQ_OK 0
+#define MCQ_EINVAL -1       /* bad argument (shape not a power of two, null pointer, too-small buffer...) */
+#define MCQ_EUNSUPPORTED -2 /* K < 16 with N > 1 (the reference itself raises), K > 256, N > 64 */
+#define MCQ_ECUDA -3        /* a CUDA call failed; see mcq_last_error() */
+#define MCQ_ENODEVICE -4    /* no sm_100 device: there is no CPU fallback */
+
+/* element types of x / decode output */
+#define MCQ_F32 0
+#define MCQ_F16 1
+#define MCQ_BF16 2
+/* element types of index arrays */
+#define MCQ_U8 0  /* byte-packed exactly like Quantizer.encode(as_bytes=True) (:266-272) */
+#define MCQ_I64 1 /* one int64 per codebook, like as_bytes=False */
+#define MCQ_I32 2
+
+int mcq_version(void);
+const char *mcq_last_error(void);
+
+/* Number of uint8 columns Quantizer.encode(as_bytes=True) produces (:266-271): N halves while K*K <= 256. */
+int mcq_packed_cols(int num_codebooks, int codebook_size);
+
+/* Size in bytes of the prepared blob for a (N, K, D) quantizer. */
+size_t mcq_prepared_bytes(int num_codebooks, int codebook_size, int dim);
+
+/* Workspace needed by mcq_encode / mcq_refine for up to `max_frames` frames per call (larger batches
+ * are processed in chunks that fit whatever workspace is given, as long as it holds at least
+ * mcq_workspace_bytes(1024, ...)). */
+size_t mcq_workspace_bytes(int64_t max_frames, int dim, int num_codebooks, int codebook_size);
+
+/*
+ * Builds everything the kernels need from the raw parameters (all fp32, device):
+ *   centers (N,K,D); centers_scale, logits_scale: 1-element tensors (raw parameters, exp() applied here
+ *   as exp(p * scale_speed), :78, :278); to_logits_weight (N*K, D); to_logits_bias (N*K).
+ * Must be called again whenever a parameter changes.
+ */
+int mcq_prepare(const float *centers, const float *centers_scale, const float *to_logits_weight,
+                const float *to_logits_bias, const float *logits_scale, float scale_speed, int num_codebooks,
+                int codebook_size, int dim, void *prepared, size_t prepared_bytes, void *stream);
+
+/* Quantizer.encode: x (B, D) of x_dtype -> codes.  codes_dtype MCQ_U8: (B, mcq_packed_cols) bytes;
+ * MCQ_I64 / MCQ_I32: (B, N).  iters = refine_indexes_iters (reference default 5). */
+int mcq_encode(const void *x, int x_dtype, int64_t num_frames, int dim, int num_codebooks, int codebook_size,
+               const void *prepared, int iters, void *codes, int codes_dtype, void *workspace,
+               size_t workspace_bytes, void *stream);
+
+/* `iters` passes of Quantizer._refine_indexes starting from idx_in (B, N) int64 -> idx_out (B, N) int64
+ * (may alias idx_in). */
+int mcq_refine(const void *x, int x_dtype, int64_t num_frames, int dim, int num_codebooks, int codebook_size,
+               const void *prepared, int iters, const int64_t *idx_in, int64_t *idx_out, void *workspace,
+               size_t workspace_bytes, void *stream);
+
+/* Quantizer.decode: codes (B, ncols) of codes_dtype (ncols == N, or a packed column count dividing N)
+ * -> out (B, D) of out_dtype.  Sums the selected scaled centers in codebook order n = 0..N-1 in fp32. */
+int mcq_decode(const void *codes, int codes_dtype, int64_t num_frames, int ncols, int num_codebooks,
+               int codebook_size, int dim, const void *prepared, void *out, int out_dtype, void *stream);
+
+/* Same as mcq_decode, but gathers from a caller-supplied scaled-centers tensor (N, K, D) fp32 instead of the
+ * prepared blob (the training path: the tensor autograd differentiates, quantization.py:141). */
+int mcq_decode_centers(const void *codes, int codes_dtype, int64_t num_frames, int ncols, int num_codebooks,
+                       int codebook_size, int dim, const float *scaled_centers, void *out, int out_dtype,
+                       void *stream);
+
+/* Gradient of decode w.r.t. the SCALED centers: grad_scaled_centers[n, idx[b,n], :] += grad_out[b, :].
+ * grad_scaled_centers (N,K,D) fp32 must be zeroed by the caller.  idx (B, N) int64. */
+int mcq_decode_backward(const float *grad_out, const int64_t *idx, int64_t num_frames, int num_codebooks,
+                        int codebook_size, int dim, float *grad_scaled_centers, void *stream);
+
+/* Pointers into the prepared blob (device): scaled centers (N*K, D) fp32 and the Gram table (N*K, N*K). */
+const float *mcq_prepared_scaled_centers(const void *prepared, int num_codebooks, int codebook_size, int dim);
+const float *mcq_prepared_gram(const void *prepared, int num_codebooks, int codebook_size, int dim);
+
+/* Stage-level entry points (used by the tests to check each kernel against the CPU model bit for bit):
+ *   mcq_xct:    P (B, N*K) = x . scaled_centers^T
+ *   mcq_search: `iters` passes of the table-driven refinement given P and the prepared Gram table. */
+int mcq_xct(const void *x, int x_dtype, int64_t num_frames, int dim, int num_codebooks, int codebook_size,
+            const void *prepared, float *P, void *workspace, size_t workspace_bytes, void *stream);
+int mcq_search(const float *P, const float *gram, int64_t num_frames, int num_codebooks, int codebook_size,
+               int iters, const int32_t *idx_in, int32_t *idx_out, void *stream);
+
+/* Optional per-kernel timing for benchmarks: while enabled, every kernel the entry points launch is bracketed by
+ * CUDA events on its launch stream.  mcq_profile(1) enables and resets, mcq_profile(0) disables.
+ * mcq_profile_read synchronises on the recorded events and returns, per kind, total milliseconds and launch count. */
+#define MCQ_PROF_OTHER 0  /* staging, arg-max, packing */
+#define MCQ_PROF_GEMM 1   /* tcgen05 GEMMs (logits and P) */
+#define MCQ_PROF_SEARCH 2 /* the refinement search kernel */
+#define MCQ_PROF_DECODE 3
+#define MCQ_PROF_KINDS 4
+int mcq_profile(int enable);
+int mcq_profile_read(double *ms_by_kind, int64_t *launches_by_kind);
+
+/*
+ * Host-buffer encode: x_host (B, D) and codes_host live in HOST memory (pinned or pageable).  The library
+ * stages chunks through its own pinned buffers and device workspace on `device`, overlapping H2D, compute
+ * and D2H, and returns when codes_host is complete.  `prepared` is a DEVICE blob on that device.
+ */
+int mcq_encode_host(const void *x_host, int x_dtype, int64_t num_frames, int dim, int num_codebooks,
+                    int codebook_size, const void *prepared, int iters, void *codes_host, int codes_dtype,
+                    int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCQ_H_ */

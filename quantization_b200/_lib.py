@@ -1,0 +1,114 @@
+"""ctypes binding of quantization_b200/libmcq.so (C ABI declared in include/mcq.h).
+
+There is no CPU fallback and no alternative backend: if the library is missing this module raises, and every
+entry point raises when a call fails.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmcq.so")
+
+F32, F16, BF16 = 0, 1, 2
+U8, I64, I32 = 0, 1, 2
+
+_X_DTYPES = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+_IDX_DTYPES = {torch.uint8: U8, torch.int64: I64, torch.int32: I32}
+
+
+class McqError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m quantization_b200.build` "
+            "(nvcc, sm_100a).  quantization_b200 has no CPU or PyTorch fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, sz, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float
+    sigs = {
+        "mcq_version": (i32, []),
+        "mcq_last_error": (ctypes.c_char_p, []),
+        "mcq_packed_cols": (i32, [i32, i32]),
+        "mcq_prepared_bytes": (sz, [i32, i32, i32]),
+        "mcq_workspace_bytes": (sz, [i64, i32, i32, i32]),
+        "mcq_prepare": (i32, [vp, vp, vp, vp, vp, f32, i32, i32, i32, vp, sz, vp]),
+        "mcq_encode": (i32, [vp, i32, i64, i32, i32, i32, vp, i32, vp, i32, vp, sz, vp]),
+        "mcq_refine": (i32, [vp, i32, i64, i32, i32, i32, vp, i32, vp, vp, vp, sz, vp]),
+        "mcq_decode": (i32, [vp, i32, i64, i32, i32, i32, i32, vp, vp, i32, vp]),
+        "mcq_decode_centers": (i32, [vp, i32, i64, i32, i32, i32, i32, vp, vp, i32, vp]),
+        "mcq_decode_backward": (i32, [vp, vp, i64, i32, i32, i32, vp, vp]),
+        "mcq_prepared_scaled_centers": (vp, [vp, i32, i32, i32]),
+        "mcq_prepared_gram": (vp, [vp, i32, i32, i32]),
+        "mcq_xct": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, vp, sz, vp]),
+        "mcq_search": (i32, [vp, vp, i64, i32, i32, i32, vp, vp, vp]),
+        "mcq_encode_host": (i32, [vp, i32, i64, i32, i32, i32, vp, i32, vp, i32, i32]),
+        "mcq_profile": (i32, [i32]),
+        "mcq_profile_read": (i32, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)  # AttributeError here == the library does not export what mcq.h declares
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+EXPORTS = ["mcq_version", "mcq_last_error", "mcq_packed_cols", "mcq_prepared_bytes", "mcq_workspace_bytes",
+           "mcq_prepare", "mcq_encode", "mcq_refine", "mcq_decode", "mcq_decode_centers", "mcq_decode_backward",
+           "mcq_prepared_scaled_centers", "mcq_prepared_gram", "mcq_xct", "mcq_search", "mcq_encode_host",
+           "mcq_profile", "mcq_profile_read"]
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().mcq_last_error().decode(errors="replace")
+        raise McqError(f"{what} failed ({rc}): {msg}")
+
+
+def x_dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _X_DTYPES[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"unsupported dtype {t.dtype}: expected float32, float16 or bfloat16") from None
+
+
+def idx_dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _IDX_DTYPES[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"unsupported index dtype {t.dtype}: expected uint8, int32 or int64") from None
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what} is on {t.device}: quantization_b200 runs on CUDA (sm_100a) only and has no CPU fallback")
+
+
+PROF_KINDS = ("other", "gemm", "search", "decode")
+
+
+def profile(enable: bool):
+    check(lib().mcq_profile(1 if enable else 0), "mcq_profile")
+
+
+def profile_read():
+    """{kind: (total_ms, launches)} of the kernels launched since profile(True)."""
+    ms = (ctypes.c_double * 4)()
+    n = (ctypes.c_int64 * 4)()
+    check(lib().mcq_profile_read(ms, n), "mcq_profile_read")
+    return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(PROF_KINDS)}

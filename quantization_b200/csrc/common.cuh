@@ -1,0 +1,88 @@
+// common.cuh -- shared declarations of libmcq.so (sm_100a only; there is no CPU fallback).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/mcq.h"
+
+namespace mcq {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define MCQ_CUDA(call)                                            \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return ::mcq::cuda_fail(e__, #call); \
+    } while (0)
+
+#define MCQ_LAUNCH_CHECK(what)                                        \
+    do {                                                              \
+        cudaError_t e__ = cudaGetLastError();                         \
+        if (e__ != cudaSuccess) return ::mcq::cuda_fail(e__, what);   \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline bool is_pow2(long v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// Layout of the caller-owned prepared blob (device memory).  All offsets are multiples of 1024 bytes.
+struct Prepared {
+    int N, K, D, NK;
+    int Dp;  // D rounded up to a multiple of 64: row length of the bf16 split operands
+    size_t off_cs;     // float [NK*D]   scaled centers  exp(centers_scale*speed) * centers   (quantization.py:77-79)
+    size_t off_w;      // float [NK*D]   to_logits.weight (copy)
+    size_t off_bias;   // float [NK]     to_logits.bias (copy)
+    size_t off_gram;   // float [NK*NK]  G = Cs Cs^T (fp64 accumulation, rounded once)
+    size_t off_scal;   // float [4]      {centers scale, logits scale}
+    size_t off_csplit; // bf16  [3][NK*Dp] three-way bf16 split of cs (operands of the tcgen05 GEMM)
+    size_t off_wsplit; // bf16  [3][NK*Dp] three-way bf16 split of w
+    size_t bytes;
+};
+
+Prepared prepared_layout(int N, int K, int D);
+
+// Per-call workspace layout for a chunk of Bc frames.
+struct Workspace {
+    int64_t Bc;
+    int Mp;            // Bc rounded up to 128
+    size_t off_xf;     // float [Mp*D]      x as fp32 (identity for fp32 input is still copied: uniform path)
+    size_t off_xsplit; // bf16  [3][Mp*Dp]  split of x
+    size_t off_lsplit; // bf16  [3][Mp*Dp]  split of fl(logits_scale * x)
+    size_t off_p;      // float [Mp*NK]     P = x Cs^T   (also receives the logits before P is formed)
+    size_t off_idx;    // int32 [Mp*N]
+    size_t bytes;
+};
+
+Workspace workspace_layout(int64_t Bc, int N, int K, int D);
+
+int check_shape(int N, int K, int D);
+
+// ---- kernel launchers (each enqueues on `st` and returns MCQ_OK or an error) -------------------------------------
+int launch_prepare(const float *centers, const float *centers_scale, const float *w, const float *bias,
+                   const float *logits_scale, float scale_speed, const Prepared &L, char *blob, cudaStream_t st);
+// x (any dtype) -> fp32 copy, bf16 splits of x and of fl(lscale * x)
+int launch_split_x(const void *x, int x_dtype, int64_t B, const Prepared &L, const char *blob, const Workspace &W,
+                   char *ws, bool want_logits_split, cudaStream_t st);
+// C (M, NK) = A (M, D) . Bm (NK, D)^T  plain fp32 FFMA version (scaffolding / cross-check of the tcgen05 GEMM)
+int launch_gemm_ffma(const float *A, const float *Bm, float *C, int64_t M, int NK, int D, const float *a_scale,
+                     cudaStream_t st);
+// bf16x3 tcgen05 GEMM: C (M, NK) fp32 = sum of the six leading products of the split operands
+int launch_gemm_tc(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, float *C, int64_t Mp, int NK, int Dp,
+                   cudaStream_t st);
+int launch_argmax_init(const float *logits, const float *bias, int64_t B, int N, int K, int32_t *idx, cudaStream_t st);
+int launch_search(const float *P, const float *gram, int64_t B, int N, int K, int iters, const int32_t *idx_in,
+                  int32_t *idx_out, cudaStream_t st);
+int launch_pack(const int32_t *idx, int64_t B, int N, int K, void *codes, int codes_dtype, cudaStream_t st);
+int launch_i64_to_i32(const int64_t *src, int32_t *dst, int64_t n, int K, cudaStream_t st);
+int launch_i32_to_i64(const int32_t *src, int64_t *dst, int64_t n, cudaStream_t st);
+int launch_decode(const void *codes, int codes_dtype, int64_t B, int ncols, int N, int K, int D, const float *cs,
+                  void *out, int out_dtype, cudaStream_t st);
+int launch_decode_backward(const float *grad_out, const int64_t *idx, int64_t B, int N, int K, int D, float *grad,
+                           cudaStream_t st);
+
+bool use_tensor_core_gemm();
+
+}  // namespace mcq

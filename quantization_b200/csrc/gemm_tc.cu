@@ -1,0 +1,345 @@
+// gemm_tc.cu -- fp32-faithful GEMM on the 5th-generation tensor cores:  C (Mp, NK) fp32 = A (Mp, D) . B (NK, D)^T
+// with both operands given as exact three-way bf16 splits a = a0 + a1 + a2 (8 significand bits each).
+// The six leading cross products  a0b0 + a0b1 + a1b0 + a0b2 + a1b1 + a2b0  are issued as tcgen05.mma kind::f16
+// (bf16 in, fp32 accumulate in TMEM); the dropped terms are below 2^-23 of |a||b| per element, i.e. under the
+// rounding noise of the fp32 accumulation itself.  A single-pass bf16 or tf32 GEMM flips 0.1-7 % of the codes
+// (SURVEY.md section 0 fact 3), which is why the split is there.
+//
+// This replaces the reference's `to_logits(x)` addmm (quantization.py:279) and the per-pass scoring matmul
+// (quantization.py:413-416; here done once per frame as P = x Cs^T, see search.cu).
+//
+// Structure: persistent CTAs (one per SM), 128 x BN output tile, K blocks of 64 bf16 (one 128-byte swizzle atom).
+//   warp 0      TMA producer: per K block 3 A-plane boxes + 3 B-plane boxes -> 128B-swizzled smem, 2-stage ring
+//   warp 1      TMEM allocator + single-thread MMA issuer (24 tcgen05.mma per K block), tcgen05.commit -> mbarriers
+//   warps 2..5  epilogue: tcgen05.ld 32x32b.x32 -> registers -> 16-byte global stores, overlapped with the next
+//               tile's MMAs through a double-buffered TMEM accumulator
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mcq {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // bf16 elements = 128 bytes = one swizzle atom row
+constexpr int STAGES = 2;
+constexpr int NUM_THREADS = 192;
+
+template <int BN>
+struct TcCfg {
+    static constexpr uint32_t A_PLANE = BM * 128;  // bytes of one plane of the A stage
+    static constexpr uint32_t B_PLANE = BN * 128;
+    static constexpr uint32_t STAGE = 3 * A_PLANE + 3 * B_PLANE;
+    static constexpr uint32_t SMEM = STAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    // Two fp32 accumulators per tile -- `main` takes only the a0*b0 products, `corr` the five small cross terms --
+    // double buffered.  The tensor core truncates when it adds into the accumulator, so every MMA costs up to an
+    // ulp of |acc|; keeping the 5/6 of the MMAs that carry < 2^-8 of the magnitude out of the main accumulator
+    // cuts that bias six-fold (measured: 1.3e-6 -> see profiles/gemm_accuracy.md, relative to sum|x_d c_d|).
+    static constexpr uint32_t TMEM_COLS = 4 * BN;
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M   (cute::UMMA::InstrDescriptor bit layout)
+    static constexpr uint32_t IDESC =
+        (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+// K-major, 128-byte swizzle, rows of exactly 128 bytes: SBO = 8 rows * 128 B, LBO unused (1), descriptor version 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// the six products kept (plane of A, plane of B): five corrections, smallest first, then the main product
+__device__ constexpr int kProdA[6] = {2, 1, 0, 1, 0, 0};
+__device__ constexpr int kProdB[6] = {0, 1, 2, 0, 1, 0};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                   float *__restrict__ C, int m_tiles, int n_tiles, int k_blocks, int ldc, int a_plane_rows,
+                   int b_plane_rows) {
+    using Cfg = TcCfg<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = base + STAGES * Cfg::STAGE;
+    // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base address word
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t *tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = m_tiles * n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"(Cfg::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t st = base + s * Cfg::STAGE;
+                    mbar_expect_tx(full_bar(s), Cfg::STAGE);
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        tma_load_2d(st + p * Cfg::A_PLANE, &tma_a, kb * BK, p * a_plane_rows + m0, full_bar(s));
+                        tma_load_2d(st + 3 * Cfg::A_PLANE + p * Cfg::B_PLANE, &tma_b, kb * BK, p * b_plane_rows + n0,
+                                    full_bar(s));
+                    }
+                    if (++s == STAGES) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            int s = 0;
+            uint32_t ph = 0;
+            int acc = 0;
+            uint32_t aph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), aph ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_main = tmem_base + (uint32_t)(acc * 2 * BN);
+                const uint32_t tmem_corr = tmem_main + (uint32_t)BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = base + s * Cfg::STAGE;
+#pragma unroll
+                    for (int pr = 0; pr < 6; ++pr) {
+                        const uint32_t a_addr = st + kProdA[pr] * Cfg::A_PLANE;
+                        const uint32_t b_addr = st + 3 * Cfg::A_PLANE + kProdB[pr] * Cfg::B_PLANE;
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            if (pr == 5)
+                                umma_bf16(tmem_main, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32),
+                                          Cfg::IDESC, (kb | k) != 0 ? 1u : 0u);
+                            else
+                                umma_bf16(tmem_corr, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32),
+                                          Cfg::IDESC, (kb | pr | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+                    if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
+                    if (++s == STAGES) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    aph ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+            mbar_wait(tfull_bar(acc), aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float *crow = C + (size_t)(m0 + q * 32 + lane) * ldc + n0;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32], rc[32];
+                const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
+                tmem_ld32(lane_base, r);
+                tmem_ld32(lane_base + (uint32_t)BN, rc);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    float4 o;
+                    o.x = __uint_as_float(r[4 * v + 0]) + __uint_as_float(rc[4 * v + 0]);
+                    o.y = __uint_as_float(r[4 * v + 1]) + __uint_as_float(rc[4 * v + 1]);
+                    o.z = __uint_as_float(r[4 * v + 2]) + __uint_as_float(rc[4 * v + 2]);
+                    o.w = __uint_as_float(r[4 * v + 3]) + __uint_as_float(rc[4 * v + 3]);
+                    *reinterpret_cast<float4 *>(crow + c * 32 + 4 * v) = o;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) {
+                acc = 0;
+                aph ^= 1u;
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS)
+                     : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return MCQ_ECUDA;
+    }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * sizeof(__nv_bfloat16)};
+    cuuint32_t box[2] = {BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed: %d (rows=%llu cols=%llu box=%u)", (int)r, (unsigned long long)rows,
+                  (unsigned long long)cols, box_rows);
+        return MCQ_ECUDA;
+    }
+    return MCQ_OK;
+}
+
+template <int BN>
+int launch_bn(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, float *C, int64_t Mp, int NK, int Dp,
+              cudaStream_t st) {
+    using Cfg = TcCfg<BN>;
+    const uint64_t NKp = align_up((size_t)NK, 128);
+    CUtensorMap ma, mb;
+    int rc;
+    if ((rc = make_map(&ma, a_split, 3ull * (uint64_t)Mp, (uint64_t)Dp, BM))) return rc;
+    if ((rc = make_map(&mb, b_split, 3ull * NKp, (uint64_t)Dp, BN))) return rc;
+    auto kern = gemm_bf16x3_kernel<BN>;
+    MCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    int dev = 0, sms = 148;
+    MCQ_CUDA(cudaGetDevice(&dev));
+    MCQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int m_tiles = (int)(Mp / BM), n_tiles = NK / BN;
+    int64_t tiles = (int64_t)m_tiles * n_tiles;
+    int grid = (int)(tiles < sms ? tiles : sms);
+    kern<<<grid, NUM_THREADS, Cfg::SMEM, st>>>(ma, mb, C, m_tiles, n_tiles, Dp / BK, NK, (int)Mp, (int)NKp);
+    MCQ_LAUNCH_CHECK("gemm_bf16x3_kernel");
+    return MCQ_OK;
+}
+
+}  // namespace
+
+int launch_gemm_tc(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, float *C, int64_t Mp, int NK, int Dp,
+                   cudaStream_t st) {
+    if (Mp <= 0) return MCQ_OK;
+    if (Mp % BM != 0 || Dp % BK != 0 || NK % 64 != 0) {
+        set_error("gemm_tc: Mp=%lld Dp=%d NK=%d not tile aligned", (long long)Mp, Dp, NK);
+        return MCQ_EINVAL;
+    }
+    if (NK % 128 == 0) return launch_bn<128>(a_split, b_split, C, Mp, NK, Dp, st);
+    return launch_bn<64>(a_split, b_split, C, Mp, NK, Dp, st);
+}
+
+}  // namespace mcq

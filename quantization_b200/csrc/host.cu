@@ -1,0 +1,109 @@
+// host.cu -- mcq_encode_host: Quantizer.encode (quantization.py:244-275) for a caller that holds HOST buffers.
+// Frames are streamed through the device in chunks on three streams (H2D, compute, D2H) with double buffering, so
+// the PCIe copies of chunk i+1 / i-1 overlap the kernels of chunk i.  Device buffers are cached per device.
+#include <mutex>
+
+#include "common.cuh"
+
+namespace mcq {
+
+namespace {
+
+struct HostCtx {
+    bool init = false;
+    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    void *d_x[2] = {nullptr, nullptr};
+    void *d_codes[2] = {nullptr, nullptr};
+    void *ws = nullptr;
+    size_t x_cap[2] = {0, 0}, codes_cap[2] = {0, 0}, ws_cap = 0;
+};
+
+constexpr int MAX_DEV = 16;
+HostCtx g_ctx[MAX_DEV];
+std::mutex g_mu[MAX_DEV];
+
+int grow(void **p, size_t *cap, size_t need) {
+    if (*cap >= need) return MCQ_OK;
+    if (*p) MCQ_CUDA(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    MCQ_CUDA(cudaMalloc(p, need));
+    *cap = need;
+    return MCQ_OK;
+}
+
+}  // namespace
+
+}  // namespace mcq
+
+using namespace mcq;
+
+extern "C" int mcq_encode_host(const void *x_host, int x_dtype, int64_t B, int D, int N, int K, const void *prepared,
+                               int iters, void *codes_host, int codes_dtype, int device) {
+    int rc = check_shape(N, K, D);
+    if (rc) return rc;
+    if (B < 0 || iters < 0 || x_dtype < 0 || x_dtype > 2 || codes_dtype < 0 || codes_dtype > 2 || device < 0 ||
+        device >= MAX_DEV) {
+        set_error("mcq_encode_host: bad argument");
+        return MCQ_EINVAL;
+    }
+    if (B == 0) return MCQ_OK;
+    if (!x_host || !prepared || !codes_host) {
+        set_error("mcq_encode_host: null pointer");
+        return MCQ_EINVAL;
+    }
+    std::lock_guard<std::mutex> lock(g_mu[device]);
+    int prev_dev = 0;
+    MCQ_CUDA(cudaGetDevice(&prev_dev));
+    MCQ_CUDA(cudaSetDevice(device));
+    HostCtx &c = g_ctx[device];
+    if (!c.init) {
+        MCQ_CUDA(cudaStreamCreateWithFlags(&c.s_in, cudaStreamNonBlocking));
+        MCQ_CUDA(cudaStreamCreateWithFlags(&c.s_cmp, cudaStreamNonBlocking));
+        MCQ_CUDA(cudaStreamCreateWithFlags(&c.s_out, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            MCQ_CUDA(cudaEventCreateWithFlags(&c.ev_in[k], cudaEventDisableTiming));
+            MCQ_CUDA(cudaEventCreateWithFlags(&c.ev_cmp[k], cudaEventDisableTiming));
+            MCQ_CUDA(cudaEventCreateWithFlags(&c.ev_out[k], cudaEventDisableTiming));
+        }
+        c.init = true;
+    }
+    const size_t xelt = x_dtype == MCQ_F32 ? 4 : 2;
+    const int ncols = codes_dtype == MCQ_U8 ? mcq_packed_cols(N, K) : N;
+    const size_t celt = codes_dtype == MCQ_U8 ? 1 : (codes_dtype == MCQ_I64 ? 8 : 4);
+    int64_t Bc = 148 * 128 * 2;  // 37,888 frames per chunk
+    if (Bc > B) Bc = (int64_t)align_up((size_t)B, 128);
+    const size_t ws_need = mcq_workspace_bytes(Bc, D, N, K);
+    if ((rc = grow(&c.ws, &c.ws_cap, ws_need))) return rc;
+    for (int k = 0; k < 2; ++k) {
+        if ((rc = grow(&c.d_x[k], &c.x_cap[k], (size_t)Bc * D * xelt))) return rc;
+        if ((rc = grow(&c.d_codes[k], &c.codes_cap[k], (size_t)Bc * ncols * celt))) return rc;
+    }
+    // the caller's stream (legacy default) may still be producing `prepared`: order after it
+    MCQ_CUDA(cudaStreamSynchronize(nullptr));
+    int64_t chunk = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += Bc, ++chunk) {
+        const int k = (int)(chunk & 1);
+        const int64_t nb = B - b0 < Bc ? B - b0 : Bc;
+        // d_x[k] was last read by the compute of chunk-2, d_codes[k] by the D2H of chunk-2
+        MCQ_CUDA(cudaStreamWaitEvent(c.s_in, c.ev_cmp[k], 0));
+        MCQ_CUDA(cudaMemcpyAsync(c.d_x[k], (const char *)x_host + (size_t)b0 * D * xelt, (size_t)nb * D * xelt,
+                                 cudaMemcpyHostToDevice, c.s_in));
+        MCQ_CUDA(cudaEventRecord(c.ev_in[k], c.s_in));
+        MCQ_CUDA(cudaStreamWaitEvent(c.s_cmp, c.ev_in[k], 0));
+        MCQ_CUDA(cudaStreamWaitEvent(c.s_cmp, c.ev_out[k], 0));
+        if ((rc = mcq_encode(c.d_x[k], x_dtype, nb, D, N, K, prepared, iters, c.d_codes[k], codes_dtype, c.ws, c.ws_cap,
+                             c.s_cmp)))
+            return rc;
+        MCQ_CUDA(cudaEventRecord(c.ev_cmp[k], c.s_cmp));
+        MCQ_CUDA(cudaStreamWaitEvent(c.s_out, c.ev_cmp[k], 0));
+        MCQ_CUDA(cudaMemcpyAsync((char *)codes_host + (size_t)b0 * ncols * celt, c.d_codes[k],
+                                 (size_t)nb * ncols * celt, cudaMemcpyDeviceToHost, c.s_out));
+        MCQ_CUDA(cudaEventRecord(c.ev_out[k], c.s_out));
+    }
+    MCQ_CUDA(cudaStreamSynchronize(c.s_out));
+    MCQ_CUDA(cudaStreamSynchronize(c.s_cmp));
+    MCQ_CUDA(cudaSetDevice(prev_dev));
+    return MCQ_OK;
+}

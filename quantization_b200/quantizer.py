@@ -1,0 +1,337 @@
+"""`Quantizer`: the reference's additive multi-codebook quantizer (danpovey/quantization,
+quantization/quantization.py:16-573) with the hot path -- `encode`, `decode`, `_compute_indexes`,
+`_refine_indexes` -- executed by the sm_100a kernels of libmcq.so instead of ATen ops.
+
+The class keeps the reference's constructor, parameter names / state_dict keys (`centers`, `logits_scale`,
+`centers_scale`, `id_buf`, `to_logits.weight`, `to_logits.bias`), RNG call order and method signatures, so it is a
+drop-in for that path.  Everything that is not on the hot path (loss arithmetic, diagnostics) stays in PyTorch.
+Extensions over the reference (documented in DESIGN.md): float16 / bfloat16 `x` is accepted (the reference raises on
+mixed dtypes; the kernels up-convert exactly, so the result equals the reference on `x.float()`), and
+`encode_host()` takes host tensors.
+"""
+import binascii
+import ctypes
+import math
+import os
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+
+
+def _is_power_of_two(n: int) -> bool:
+    return n > 0 and (n & (n - 1)) == 0
+
+
+class _DecodeFn(torch.autograd.Function):
+    """decode as a differentiable function of the scaled centers (reference: gather + sum, quantization.py:138-147)."""
+
+    @staticmethod
+    def forward(ctx, scaled_centers: Tensor, indexes: Tensor) -> Tensor:
+        N, K, D = scaled_centers.shape
+        B = indexes.shape[0]
+        cs = scaled_centers.detach().contiguous()
+        out = torch.empty(B, D, dtype=torch.float32, device=cs.device)
+        L = _lib.lib()
+        rc = L.mcq_decode_centers(indexes.data_ptr(), _lib.I64, B, N, N, K, D, cs.data_ptr(), out.data_ptr(),
+                                  _lib.F32, _lib.stream_ptr(cs.device))
+        _lib.check(rc, "mcq_decode_centers")
+        ctx.save_for_backward(indexes)
+        ctx.shape = (N, K, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        (indexes,) = ctx.saved_tensors
+        N, K, D = ctx.shape
+        g = grad_out.contiguous().float()
+        grad = torch.zeros(N, K, D, dtype=torch.float32, device=g.device)
+        L = _lib.lib()
+        rc = L.mcq_decode_backward(g.data_ptr(), indexes.data_ptr(), indexes.shape[0], N, K, D, grad.data_ptr(),
+                                   _lib.stream_ptr(g.device))
+        _lib.check(rc, "mcq_decode_backward")
+        return grad, None
+
+
+class Quantizer(nn.Module):
+    def __init__(self, dim: int, codebook_size: int, num_codebooks: int):
+        """Trainable quantizer encoding a `dim`-vector as `num_codebooks` integers in [0, codebook_size)
+        (reference quantization.py:20-55; same parameters, same torch-RNG consumption)."""
+        super().__init__()
+        self.dim = dim
+        self.codebook_size = codebook_size
+        self.num_codebooks = num_codebooks
+        assert _is_power_of_two(codebook_size)
+        assert _is_power_of_two(num_codebooks)
+
+        self.to_logits = nn.Linear(dim, codebook_size * num_codebooks)
+        self.centers = nn.Parameter(
+            self.to_logits.weight.detach().clone().reshape(num_codebooks, codebook_size, dim))
+        self.logits_scale = nn.Parameter(torch.zeros(()))
+        self.centers_scale = nn.Parameter(torch.zeros(()))
+        self.scale_speed = 10.0
+
+        id_bytes = binascii.b2a_hex(os.urandom(4))
+        self.id_str = id_bytes.decode("utf-8")
+        self.register_buffer("id_buf", torch.tensor(list(id_bytes), dtype=torch.uint8))
+
+        self._prep_key = None
+        self._prep_blob: Optional[Tensor] = None
+        self._ws: Optional[Tensor] = None
+
+    # ------------------------------------------------------------------ bookkeeping (reference :57-79)
+    def load_state_dict(self, *args, **kwargs):
+        ret = super().load_state_dict(*args, **kwargs)
+        self.id_str = bytes(self.id_buf.tolist()).decode("utf-8")
+        return ret
+
+    def get_id(self) -> str:
+        return self.id_str
+
+    def show_init_invocation(self) -> str:
+        return (f"quantization.Quantizer(dim={self.dim}, codebook_size={self.codebook_size}, "
+                f"num_codebooks={self.num_codebooks})")
+
+    def get_data_mean(self) -> Tensor:
+        return self.get_centers().mean(dim=1).sum(dim=0).detach()
+
+    def get_centers(self) -> Tensor:
+        scale = (self.centers_scale * self.scale_speed).exp()
+        return scale * self.centers
+
+    # ------------------------------------------------------------------ device-side prepared state
+    def _params(self):
+        return (self.centers, self.centers_scale, self.to_logits.weight, self.to_logits.bias, self.logits_scale)
+
+    def _prepared(self) -> Tensor:
+        """The prepared blob (scaled centers, Gram table, operand splits), rebuilt when any parameter changes."""
+        ps = self._params()
+        dev = self.centers.device
+        _lib.require_cuda(self.centers, "Quantizer parameters")
+        key = (dev, float(self.scale_speed)) + tuple((p.data_ptr(), p._version) for p in ps)
+        if key != self._prep_key or self._prep_blob is None:
+            for p in ps:
+                if p.dtype != torch.float32:
+                    raise RuntimeError("Quantizer parameters must be float32 (the reference's .half()/.bfloat16() "
+                                       "quantizer is a different numerical function and is not supported)")
+            L = _lib.lib()
+            N, K, D = self.num_codebooks, self.codebook_size, self.dim
+            nbytes = L.mcq_prepared_bytes(N, K, D)
+            if nbytes == 0:
+                _lib.check(-1, "mcq_prepared_bytes")
+            if self._prep_blob is None or self._prep_blob.numel() < nbytes or self._prep_blob.device != dev:
+                self._prep_blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            c, cs, w, b, ls = (p.detach().contiguous() for p in ps)
+            with torch.cuda.device(dev):
+                rc = L.mcq_prepare(c.data_ptr(), cs.data_ptr(), w.data_ptr(), b.data_ptr(), ls.data_ptr(),
+                                   float(self.scale_speed), N, K, D, self._prep_blob.data_ptr(), nbytes,
+                                   _lib.stream_ptr(dev))
+            _lib.check(rc, "mcq_prepare")
+            self._prep_key = key
+        return self._prep_blob
+
+    def _workspace(self, num_frames: int) -> Tensor:
+        L = _lib.lib()
+        need = L.mcq_workspace_bytes(max(int(num_frames), 1), self.dim, self.num_codebooks, self.codebook_size)
+        dev = self.centers.device
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        return self._ws
+
+    def _check_x(self, x: Tensor) -> Tensor:
+        _lib.require_cuda(x, "x")
+        if x.device != self.centers.device:
+            raise RuntimeError(f"x is on {x.device} but the quantizer is on {self.centers.device}")
+        _lib.x_dtype_code(x)
+        return x.contiguous()
+
+    # ------------------------------------------------------------------ hot path
+    def _encode_2d(self, x: Tensor, iters: int, codes_dtype: int) -> Tensor:
+        x = self._check_x(x)
+        B = x.shape[0]
+        N, K, D = self.num_codebooks, self.codebook_size, self.dim
+        L = _lib.lib()
+        blob = self._prepared()
+        if codes_dtype == _lib.U8:
+            out = torch.empty(B, L.mcq_packed_cols(N, K), dtype=torch.uint8, device=x.device)
+        else:
+            out = torch.empty(B, N, dtype=torch.int64, device=x.device)
+        if B == 0:
+            return out
+        ws = self._workspace(B)
+        with torch.cuda.device(x.device):
+            rc = L.mcq_encode(x.data_ptr(), _lib.x_dtype_code(x), B, D, N, K, blob.data_ptr(), int(iters),
+                              out.data_ptr(), codes_dtype, ws.data_ptr(), ws.numel(), _lib.stream_ptr(x.device))
+        _lib.check(rc, "mcq_encode")
+        return out
+
+    def encode(self, x: Tensor, refine_indexes_iters: int = 5, as_bytes: bool = True) -> Tensor:
+        """Reference quantization.py:244-275.  x (*, dim) -> uint8 (*, N_packed) if as_bytes else int64 (*, N)."""
+        x2 = x.reshape(-1, self.dim)
+        codes = self._encode_2d(x2, refine_indexes_iters, _lib.U8 if as_bytes else _lib.I64)
+        return codes.reshape(*x.shape[:-1], codes.shape[-1])
+
+    def encode_host(self, x: Tensor, refine_indexes_iters: int = 5, as_bytes: bool = True,
+                    out: Optional[Tensor] = None) -> Tensor:
+        """Extension: `x` (*, dim) lives in HOST memory (ideally pinned); returns host codes.  Chunks are streamed
+        through the device with copies overlapping the kernels (mcq_encode_host)."""
+        if x.is_cuda:
+            raise RuntimeError("encode_host expects a host tensor; use encode() for device tensors")
+        x2 = x.reshape(-1, self.dim).contiguous()
+        B = x2.shape[0]
+        N, K, D = self.num_codebooks, self.codebook_size, self.dim
+        L = _lib.lib()
+        blob = self._prepared()
+        dev = self.centers.device
+        cols = L.mcq_packed_cols(N, K) if as_bytes else N
+        dt = torch.uint8 if as_bytes else torch.int64
+        if out is None:
+            out = torch.empty(B, cols, dtype=dt, pin_memory=True)
+        assert out.shape == (B, cols) and out.dtype == dt and out.is_contiguous() and not out.is_cuda
+        torch.cuda.current_stream(dev).synchronize()  # the blob may just have been rebuilt on this stream
+        rc = L.mcq_encode_host(x2.data_ptr(), _lib.x_dtype_code(x2), B, D, N, K, blob.data_ptr(),
+                               int(refine_indexes_iters), out.data_ptr(), _lib.U8 if as_bytes else _lib.I64,
+                               dev.index if dev.index is not None else torch.cuda.current_device())
+        _lib.check(rc, "mcq_encode_host")
+        return out.reshape(*x.shape[:-1], cols)
+
+    def _compute_indexes(self, x: Tensor, refine_indexes_iters: int = 3) -> Tensor:
+        """Reference quantization.py:281-305: classifier arg-max, then `refine_indexes_iters` refinement passes."""
+        assert x.ndim == 2 and x.shape[1] == self.dim
+        return self._encode_2d(x, refine_indexes_iters, _lib.I64)
+
+    def _refine_indexes(self, x: Tensor, indexes: Tensor) -> Tensor:
+        """One pass of the reference's hierarchical pairwise search (quantization.py:308-547)."""
+        return self._refine(x, indexes, 1)
+
+    def _refine(self, x: Tensor, indexes: Tensor, iters: int) -> Tensor:
+        x = self._check_x(x)
+        assert x.ndim == 2 and x.shape[1] == self.dim
+        B = x.shape[0]
+        N, K, D = self.num_codebooks, self.codebook_size, self.dim
+        assert indexes.shape == (B, N)
+        idx = indexes.to(dtype=torch.int64, device=x.device).contiguous()
+        out = torch.empty_like(idx)
+        if B == 0:
+            return out
+        L = _lib.lib()
+        blob = self._prepared()
+        ws = self._workspace(B)
+        with torch.cuda.device(x.device):
+            rc = L.mcq_refine(x.data_ptr(), _lib.x_dtype_code(x), B, D, N, K, blob.data_ptr(), int(iters),
+                              idx.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(x.device))
+        _lib.check(rc, "mcq_refine")
+        return out
+
+    def decode(self, indexes: Tensor) -> Tensor:
+        """Reference quantization.py:117-148.  indexes (*, n) with n == num_codebooks or a packed column count
+        -> (*, dim) float32: the sum of the selected scaled centers."""
+        orig_shape = indexes.shape
+        idx = indexes.reshape(-1, indexes.shape[-1])
+        _lib.require_cuda(idx, "indexes")
+        if idx.dtype not in (torch.uint8, torch.int32, torch.int64):
+            idx = idx.to(torch.int64)
+        idx = idx.contiguous()
+        B, ncols = idx.shape
+        N, K, D = self.num_codebooks, self.codebook_size, self.dim
+        if ncols != N:
+            r = N // max(ncols, 1)
+            assert ncols > 0 and N % ncols == 0 and r in (2, 4, 8, 16)  # reference :566
+        if idx.dtype != torch.uint8 and B > 0:
+            hi = K ** (N // ncols)
+            if bool(((idx < 0) | (idx >= hi)).any()):
+                raise IndexError(f"decode: indexes out of range [0, {hi})")
+        needs_grad = torch.is_grad_enabled() and (self.centers.requires_grad or self.centers_scale.requires_grad)
+        if needs_grad and ncols == N:
+            out = _DecodeFn.apply(self.get_centers(), idx.to(torch.int64))
+        else:
+            L = _lib.lib()
+            blob = self._prepared()
+            out = torch.empty(B, D, dtype=torch.float32, device=idx.device)
+            if B > 0:
+                with torch.cuda.device(idx.device):
+                    rc = L.mcq_decode(idx.data_ptr(), _lib.idx_dtype_code(idx), B, ncols, N, K, D, blob.data_ptr(),
+                                      out.data_ptr(), _lib.F32, _lib.stream_ptr(idx.device))
+                _lib.check(rc, "mcq_decode")
+        return out.reshape(*orig_shape[:-1], D)
+
+    def _maybe_separate_indexes(self, indexes: Tensor) -> Tensor:
+        """Reference quantization.py:551-573 (kept for API completeness; decode unpacks inside its kernel)."""
+        n = indexes.shape[1]
+        if n == self.num_codebooks:
+            return indexes
+        r = self.num_codebooks // n
+        assert r in (2, 4, 8, 16)
+        K = self.codebook_size
+        powers = K ** torch.arange(r, device=indexes.device)
+        return ((indexes.unsqueeze(2).to(torch.int64) // powers) % K).reshape(indexes.shape[0], self.num_codebooks)
+
+    # ------------------------------------------------------------------ training-side (PyTorch; reference :184-242)
+    def compute_loss(self, x: Tensor, refine_indexes_iters: int = 0):
+        """Returns (rel_reconstruction_loss, logprob_loss, logits_entropy_loss, index_entropy_loss) exactly as the
+        reference defines them (quantization.py:184-242); only the index search and the decode gather run in the
+        CUDA library (the search carries no gradient in the reference either)."""
+        x = x.reshape(-1, self.dim)
+        with torch.no_grad():
+            indexes = self._compute_indexes(x, refine_indexes_iters)
+        xf = x.float() if x.dtype != torch.float32 else x
+        needs_grad = torch.is_grad_enabled() and (self.centers.requires_grad or self.centers_scale.requires_grad)
+        if needs_grad:
+            x_approx = _DecodeFn.apply(self.get_centers(), indexes)
+        else:
+            x_approx = self.decode(indexes)
+        tot_error = x_approx - xf
+        rel_reconstruction_loss = (tot_error ** 2).sum() / (((xf - self.get_data_mean()) ** 2).sum() + 1.0e-20)
+
+        N, K = self.num_codebooks, self.codebook_size
+        logits = self._logits(xf).reshape(-1, N, K).log_softmax(dim=2)
+        chosen = torch.gather(logits, dim=2, index=indexes.unsqueeze(2))
+        logprob_loss = -chosen.mean()
+
+        B = xf.shape[0]
+        counts = torch.zeros(B, N, K, device=xf.device)
+        counts.scatter_(dim=2, index=indexes.unsqueeze(2), value=1.0)
+        avg_counts = counts.mean(dim=0) + 1.0e-20
+        index_entropy = -(avg_counts * avg_counts.log()).sum(dim=1).mean()
+
+        probs = logits.exp().mean(dim=0) + 1.0e-20
+        logits_entropy = -(probs * probs.log()).sum(dim=1).mean()
+        ref_entropy = math.log(K)
+        logits_entropy_loss = (ref_entropy - logits_entropy) / ref_entropy
+        index_entropy_loss = (ref_entropy - index_entropy) / ref_entropy
+        return rel_reconstruction_loss, logprob_loss, logits_entropy_loss, index_entropy_loss
+
+    def _logits(self, x: Tensor) -> Tensor:
+        x = (self.logits_scale * self.scale_speed).exp() * x
+        return self.to_logits(x)
+
+    def compute_codebook_correlations(self) -> Tensor:
+        """Diagnostic of reference quantization.py:150-181: normalised tr(S_i S_j) of the per-codebook
+        (mean-removed) second-moment matrices."""
+        c = self.get_centers().detach()
+        c = c - c.mean(dim=1, keepdim=True)
+        var = torch.matmul(c.transpose(1, 2), c).reshape(self.num_codebooks, self.dim * self.dim)
+        cross = torch.matmul(var, var.t())
+        norm = cross.diag() ** -0.5
+        return cross * (norm.unsqueeze(0) * norm.unsqueeze(1))
+
+    def get_product_quantizer(self) -> "Quantizer":
+        """Reference quantization.py:81-112: K -> K*K, N -> N/2, entry k1*K + k2 of output codebook c is the sum of
+        entry k1 of input codebook 2c and entry k2 of input codebook 2c+1 (weights, biases and centers alike).
+        Vectorised; the sums are the same fp32 additions the reference's triple loop performs."""
+        N, K, D = self.num_codebooks, self.codebook_size, self.dim
+        ans = Quantizer(D, K * K, N // 2).to(self.centers.device)
+        ans.apply_mask = False
+        with torch.no_grad():
+            ans.logits_scale.fill_(self.logits_scale.item())
+            ans.centers_scale.fill_(self.centers_scale.item())
+            ans.scale_speed = self.scale_speed
+            W = self.to_logits.weight.reshape(N, K, D)
+            b = self.to_logits.bias.reshape(N, K)
+            C = self.centers
+            ans.to_logits.weight.copy_((W[0::2, :, None, :] + W[1::2, None, :, :]).reshape(N // 2 * K * K, D))
+            ans.to_logits.bias.copy_((b[0::2, :, None] + b[1::2, None, :]).reshape(N // 2 * K * K))
+            ans.centers.copy_((C[0::2, :, None, :] + C[1::2, None, :, :]).reshape(N // 2, K * K, D))
+        return ans

@@ -34,3 +34,21 @@ def trained_params(gt, tag):
         logits_scale=float(gt[f"{tag}/logits_scale"]),
         id_buf=torch.from_numpy(gt[f"{tag}/id_buf"]),
     )
+
+
+def make_quantizer(D, N, K, params, device, centers_scale=0.0, logits_scale=0.0):
+    """A quantization_b200.Quantizer on `device` holding the given parameter tensors."""
+    from quantization_b200 import Quantizer
+    q = Quantizer(dim=D, codebook_size=K, num_codebooks=N)
+    with torch.no_grad():
+        q.centers.copy_(params["centers"])
+        q.to_logits.weight.copy_(params["weight"])
+        q.to_logits.bias.copy_(params["bias"])
+        q.centers_scale.fill_(centers_scale)
+        q.logits_scale.fill_(logits_scale)
+    return q.to(device)
+
+
+def search_supported(N, K):
+    """(K, N) pairs the CUDA search kernel is built for (4096-candidate merges are not)."""
+    return not (N >= 32 and K > 16)
