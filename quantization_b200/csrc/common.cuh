@@ -75,6 +75,10 @@ int launch_gemm_tc(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, f
 int launch_argmax_init(const float *logits, const float *bias, int64_t B, int N, int K, int32_t *idx, cudaStream_t st);
 int launch_search(const float *P, const float *gram, int64_t B, int N, int K, int iters, const int32_t *idx_in,
                   int32_t *idx_out, cudaStream_t st);
+// second version of the search (search2.cu): codebook_size 256, 2/4/8 codebooks
+bool search2_supports(int N, int K);
+int launch_search2(const float *P, const float *gram, int64_t B, int N, int K, int iters, const int32_t *idx_in,
+                   int32_t *idx_out, cudaStream_t st);
 int launch_pack(const int32_t *idx, int64_t B, int N, int K, void *codes, int codes_dtype, cudaStream_t st);
 int launch_i64_to_i32(const int64_t *src, int32_t *dst, int64_t n, int K, cudaStream_t st);
 int launch_i32_to_i64(const int32_t *src, int64_t *dst, int64_t n, cudaStream_t st);

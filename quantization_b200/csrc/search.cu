@@ -10,6 +10,9 @@
 // Level schedule (quantization.py:453-547), all compile-time here: keep `cut1` = 16 (8 when K <= 16) candidates per
 // codebook, then repeatedly merge neighbouring groups (Kc x Kc joint candidates) and keep cutoff(L) of them, until
 // one group is left and its best joint candidate becomes the new indexes.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace mcq {
@@ -385,6 +388,12 @@ int dispatch_n(int N, const float *P, const float *G, int64_t B, int iters, cons
 int launch_search(const float *P, const float *gram, int64_t B, int N, int K, int iters, const int32_t *idx_in,
                   int32_t *idx_out, cudaStream_t st) {
     if (B <= 0) return MCQ_OK;
+    {
+        // MCQ_SEARCH=v1 keeps the generic first version for every shape (used by the tests to cross-check)
+        const char *e = getenv("MCQ_SEARCH");
+        const bool force_v1 = e && strcmp(e, "v1") == 0;
+        if (!force_v1 && search2_supports(N, K)) return launch_search2(P, gram, B, N, K, iters, idx_in, idx_out, st);
+    }
     switch (K) {
         case 2: return dispatch_n<2>(N, P, gram, B, iters, idx_in, idx_out, st);
         case 4: return dispatch_n<4>(N, P, gram, B, iters, idx_in, idx_out, st);
