@@ -14,6 +14,9 @@
 //   * merge of single codebooks (16x16): one G gather per joint candidate; merge of codebook pairs (16x16): four;
 //     merge of codebook quads (32x32): 16x16 tables T_ab per codebook pair, folded per candidate row into
 //     E_b[i][q] = sum_a T_ab[i_a][q] -- exactly the contract's inner sum -- then dot(i,j) = sum_b E_b[i][j_b].
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace mcq {
@@ -29,13 +32,49 @@ __device__ __forceinline__ float credux_min(float v) {
     return m;
 }
 
+// Scattered 4-byte reads of G (element offsets).  A texture-object variant of these gathers (TEX data pipe instead of
+// the LSU pipe) was measured and is slower (9.3 ms vs 7.2 ms per 75,776 frames, profiles/r01_search2.md), so it is gone.
+struct GSrc {
+    const float *g;
+};
+template <bool TEX>
+__device__ __forceinline__ float gat(const GSrc &G, unsigned idx) {
+    return __ldg(G.g + idx);
+}
+
+// (a0, a1) += (b0, b1): one FADD2 (packed fp32 add, each half an IEEE round-to-nearest add)
+__device__ __forceinline__ void fadd2(float &a0, float &a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\tadd.rn.f32x2 x, x, y;\n\t"
+        "mov.b64 {%0, %1}, x;\n\t}"
+        : "+f"(a0), "+f"(a1)
+        : "f"(b0), "f"(b1));
+}
+
+// -1 if a <= b else 0 (one FSET)
+__device__ __forceinline__ int le_mask(float a, float b) {
+    int r;
+    asm("set.le.s32.f32 %0, %1, %2;" : "=r"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+constexpr int TSTR = 20;  // row stride (floats) of the 16-column tables: 80 B keeps float4 rows bank-spread
+// float offset of row p of a 16-column table: rows 8..15 are shifted by 16 floats so that a warp writing rows
+// (t, t+8) x 16 columns hits 32 distinct banks
+__device__ __forceinline__ int trow_off(int p) { return p * TSTR + ((p >> 3) << 4); }
+constexpr int TAB_FLOATS = 16 * TSTR + 16;
+
 template <int N>
 struct alignas(16) WarpMem2 {
     static constexpr int NG2 = (N >= 2) ? N / 2 : 1;  // groups after the first merge
     static constexpr int NG3 = (N >= 4) ? N / 4 : 1;  // groups after the second merge
-    float2 lists[9][32];     // per-lane sorted columns (key, flat) + one row of +inf sentinels; rows 0..7 double as E
-    float tab[16][16];       // level-1 scratch (v of the 256 candidates); T_ab of the quad merge
-    float2 out1[N][16];      // level-1 kept candidates of each codebook: (delta, k)
+    union {
+        float2 lists[9][32];  // per-lane sorted columns (key, flat) + one row of +inf sentinels
+        float es[32][TSTR];   // quad merge: E_b[i][q]  (overwrites the sentinel row; restored after the merge)
+    };
+    float tab[TAB_FLOATS];   // level-1 scratch (v of the 256 candidates); T_ab of the quad merge (trow_off)
+    float kd1[N][16];        // level-1 kept candidates of each codebook: delta ...
+    int kk[N][16];           // ... and codebook entry k
+    unsigned rowk[N][16];    // (n*K + kk[n][p]) * NK: element offset of the G row of each kept candidate
     float uv[N][N][16];      // uv[a][m][p] = G[(m,old_m), (a, kk_a[p])]
     float2 sel[32];          // result of the current selection: (key, flat), ascending
     float kd2[NG2][16];      // kept deltas / slot tuples after the first merge
@@ -43,97 +82,93 @@ struct alignas(16) WarpMem2 {
     float kd3[NG3][32];      // ... after the second merge
     unsigned kt3[NG3][32];
     int old[N];              // indexes at the start of the pass (and its result)
+    unsigned rowoff[N];      // (m*K + old[m]) * NK: element offset of the G row of each current entry
     unsigned used[8];        // quad merge: which level-1 slots of each codebook the 32+32 candidates still use
 };
 
-template <int N>
-__device__ __forceinline__ int kk_of(const WarpMem2<N> &s, int a, int slot) {
-    return __float_as_int(s.out1[a][slot].y);
-}
-
-// The R smallest of the warp's 256 candidates (8 per lane, flat index lane*8 + t), ascending by (key, flat),
-// written to s.sel[0..R).  quantization.py:474-487 (sort + keep the first K_cutoff).
+// The R smallest of the warp's 256 candidates (8 per lane; candidate t of a lane has flat index flat[t], ascending in
+// t), ascending by (key, flat), written to s.sel[0..R).  quantization.py:474-487 (sort + keep the first K_cutoff).
 template <int N, int R>
-__device__ __forceinline__ void select_sorted(WarpMem2<N> &s, const float (&key)[8], int lane) {
+__device__ __forceinline__ void select_sorted(WarpMem2<N> &s, const float (&key)[8], const int (&flat)[8], int lane) {
+    // rank of key[t] among the lane's 8 keys, equal keys in index order:
+    //   rank[t] = #{u < t: key[u] <= key[t]} + #{u > t: key[u] < key[t]}
     int rank[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) rank[t] = 0;
+    for (int t = 0; t < 8; ++t) rank[t] = 7 - t;
 #pragma unroll
     for (int t = 1; t < 8; ++t)
 #pragma unroll
         for (int u = 0; u < t; ++u) {
-            const bool le = key[u] <= key[t];  // equal keys keep index order
-            rank[t] += le ? 1 : 0;
-            rank[u] += le ? 0 : 1;
+            const int c = le_mask(key[u], key[t]);  // -1 when key[u] sorts before key[t]
+            rank[t] -= c;
+            rank[u] += c;
         }
 #pragma unroll
-    for (int t = 0; t < 8; ++t) s.lists[rank[t]][lane] = make_float2(key[t], __int_as_float(lane * 8 + t));
+    for (int t = 0; t < 8; ++t) s.lists[rank[t]][lane] = make_float2(key[t], __int_as_float(flat[t]));
     // a lane reads back only its own column: no warp synchronisation needed here
     const float2 *col = &s.lists[0][lane];
-    const unsigned lt = (1u << lane) - 1u;
-    int pos = 0;
     float2 head = col[0];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const float m = credux_min(head.x);
-        const bool p = head.x == m;
-        const unsigned b = __ballot_sync(FULL, p);
-        const bool mine = p && ((b & lt) == 0u);  // lowest lane among equals = lowest flat index
+        // among the lanes holding the minimum the lowest flat index wins (contract: ascending (key, flat))
+        const unsigned f = (head.x == m) ? (unsigned)__float_as_int(head.y) : 0x7fffffffu;
+        const bool mine = (f == __reduce_min_sync(FULL, f)) && f != 0x7fffffffu;
         if (mine) {
             s.sel[r] = head;
-            pos += 32;
+            col += 32;
+            head = *col;
         }
-        head = col[pos];
     }
     __syncwarp();
 }
 
 // Flat index of the smallest of the warp's 256 candidates (lowest flat index among equals).
-__device__ __forceinline__ int select_best(const float (&key)[8], int lane) {
+__device__ __forceinline__ int select_best(const float (&key)[8], const int (&flat)[8], int lane) {
     float best = key[0];
-    int bt = 0;
+    int bf = flat[0];
 #pragma unroll
     for (int t = 1; t < 8; ++t)
         if (key[t] < best) {
             best = key[t];
-            bt = t;
+            bf = flat[t];
         }
     const float m = credux_min(best);
-    const unsigned b = __ballot_sync(FULL, best == m);
-    const int w = b ? (__ffs(b) - 1) : 0;
-    return __shfl_sync(FULL, lane * 8 + bt, w);
+    const unsigned f = (best == m) ? (unsigned)bf : 0x7fffffffu;
+    const unsigned w = __reduce_min_sync(FULL, f);
+    return w == 0x7fffffffu ? 0 : (int)w;  // the guard is only reachable with NaN scores
 }
 
 // Level 1 (quantization.py:401-418 with the per-codebook constants dropped) + top-16 per codebook.
+// Lane L owns entries 4L..4L+3 and 128+4L..128+4L+3, so every float4 request of the warp is 512 contiguous bytes.
 template <int N>
-__device__ __forceinline__ void level1(WarpMem2<N> &s, const float *__restrict__ Pb, const float *__restrict__ G,
+__device__ __forceinline__ void level1(WarpMem2<N> &s, const float *__restrict__ Pb, const float *__restrict__ Gp,
                                        int lane) {
-    constexpr int NK = N * K2;
-    const float *diag = G + (size_t)NK * NK;
-    float *scratch = &s.tab[0][0];
+    constexpr unsigned NK = N * K2;
+    const float *diag = Gp + (size_t)NK * NK;
+    float *scratch = &s.tab[0];
+    int flat[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) flat[t] = (t < 4 ? 0 : 128 - 4) + lane * 4 + t;
 #pragma unroll 1
     for (int n = 0; n < N; ++n) {
         float acc[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) acc[t] = 0.0f;
-        const float *colbase = G + n * K2 + lane * 8;
+        const unsigned colbase = n * K2 + lane * 4;
 #pragma unroll
         for (int mm = 0; mm < N - 1; ++mm) {
             const int m = mm + (mm >= n ? 1 : 0);  // ascending m, skipping n
-            const float4 *row = reinterpret_cast<const float4 *>(colbase + (size_t)(m * K2 + s.old[m]) * NK);
-            const float4 a = __ldg(row), b = __ldg(row + 1);
-            acc[0] = acc[0] + a.x;
-            acc[1] = acc[1] + a.y;
-            acc[2] = acc[2] + a.z;
-            acc[3] = acc[3] + a.w;
-            acc[4] = acc[4] + b.x;
-            acc[5] = acc[5] + b.y;
-            acc[6] = acc[6] + b.z;
-            acc[7] = acc[7] + b.w;
+            const float4 *row = reinterpret_cast<const float4 *>(Gp + (s.rowoff[m] + colbase));
+            const float4 a = __ldg(row), b = __ldg(row + 32);
+            fadd2(acc[0], acc[1], a.x, a.y);
+            fadd2(acc[2], acc[3], a.z, a.w);
+            fadd2(acc[4], acc[5], b.x, b.y);
+            fadd2(acc[6], acc[7], b.z, b.w);
         }
-        const float4 *pp = reinterpret_cast<const float4 *>(Pb + n * K2 + lane * 8);
-        const float4 *dp = reinterpret_cast<const float4 *>(diag + n * K2 + lane * 8);
-        const float4 p0 = __ldg(pp), p1 = __ldg(pp + 1), d0 = __ldg(dp), d1 = __ldg(dp + 1);
+        const float4 *pp = reinterpret_cast<const float4 *>(Pb + colbase);
+        const float4 *dp = reinterpret_cast<const float4 *>(diag + colbase);
+        const float4 p0 = __ldg(pp), p1 = __ldg(pp + 32), d0 = __ldg(dp), d1 = __ldg(dp + 32);
         float v[8];
         v[0] = fmaf(2.0f, acc[0] - p0.x, d0.x);
         v[1] = fmaf(2.0f, acc[1] - p0.y, d0.y);
@@ -143,122 +178,149 @@ __device__ __forceinline__ void level1(WarpMem2<N> &s, const float *__restrict__
         v[5] = fmaf(2.0f, acc[5] - p1.y, d1.y);
         v[6] = fmaf(2.0f, acc[6] - p1.z, d1.z);
         v[7] = fmaf(2.0f, acc[7] - p1.w, d1.w);
-        reinterpret_cast<float4 *>(scratch)[lane * 2] = make_float4(v[0], v[1], v[2], v[3]);
-        reinterpret_cast<float4 *>(scratch)[lane * 2 + 1] = make_float4(v[4], v[5], v[6], v[7]);
+        reinterpret_cast<float4 *>(scratch)[lane] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4 *>(scratch)[32 + lane] = make_float4(v[4], v[5], v[6], v[7]);
         __syncwarp();
         const float vold = scratch[s.old[n]];
         float key[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) key[t] = v[t] - vold;
-        select_sorted<N, 16>(s, key, lane);
-        if (lane < 16) s.out1[n][lane] = s.sel[lane];  // flat index == codebook entry k
+        select_sorted<N, 16>(s, key, flat, lane);
+        if (lane < 16) {
+            const float2 r = s.sel[lane];
+            s.kd1[n][lane] = r.x;
+            s.kk[n][lane] = __float_as_int(r.y);  // flat index == codebook entry k
+            s.rowk[n][lane] = (unsigned)(n * K2 + __float_as_int(r.y)) * NK;
+        }
         __syncwarp();
     }
 }
 
-template <int N>
-__device__ __forceinline__ void gather_uv(WarpMem2<N> &s, const float *__restrict__ G, int lane) {
-    constexpr int NK = N * K2;
+template <int N, bool TEX>
+__device__ __forceinline__ void gather_uv(WarpMem2<N> &s, const GSrc &G, int lane) {
     const int p = lane & 15, mh = lane >> 4;
 #pragma unroll 1
     for (int a = 0; a < N; ++a) {
-        const float *col = G + a * K2 + kk_of<N>(s, a, p);
+        const unsigned col = a * K2 + s.kk[a][p];
 #pragma unroll
         for (int r = 0; r < N / 2; ++r) {
             const int m = 2 * r + mh;
-            if (m != a) s.uv[a][m][p] = __ldg(col + (size_t)(m * K2 + s.old[m]) * NK);
+            if (m != a) s.uv[a][m][p] = gat<TEX>(G, s.rowoff[m] + col);
         }
     }
     __syncwarp();
 }
 
 // Merge of two single codebooks e = 2g, o = 2g+1: 16 x 16 joint candidates (quantization.py:504-547 at L = 1).
-template <int N, bool FINAL>
-__device__ __forceinline__ void merge1(WarpMem2<N> &s, const float *__restrict__ G, int g, int lane) {
-    constexpr int NK = N * K2;
+// Lane (hi, j) scores candidates (i = 8*hi + t, j), t = 0..7: a request reads two G rows x 16 columns.
+template <int N, bool TEX, bool FINAL>
+__device__ __forceinline__ void merge1(WarpMem2<N> &s, const GSrc &G, int g, int lane) {
     const int e = 2 * g, o = e + 1;
-    const int i = lane >> 1, jb = (lane & 1) * 8;
-    const float2 ke = s.out1[e][i];
-    const float *rowp = G + (size_t)(e * K2 + __float_as_int(ke.y)) * NK + o * K2;
-    const float u = s.uv[e][o][i];
-    const float w = __ldg(G + (size_t)(e * K2 + s.old[e]) * NK + o * K2 + s.old[o]);
+    const int j = lane & 15, ib = (lane >> 4) * 8;
+    const unsigned ko = o * K2 + s.kk[o][j];
+    const float v = s.uv[o][e][j];
+    const float kdo = s.kd1[o][j];
+    const float w = gat<TEX>(G, s.rowoff[e] + o * K2 + s.old[o]);
+    unsigned rowp[8];
+    float u[8], kde[8];
+    {
+        const uint4 *rp = reinterpret_cast<const uint4 *>(&s.rowk[e][ib]);
+        const float4 *up = reinterpret_cast<const float4 *>(&s.uv[e][o][ib]);
+        const float4 *dp = reinterpret_cast<const float4 *>(&s.kd1[e][ib]);
+        const uint4 r0 = rp[0], r1 = rp[1];
+        const float4 u0 = up[0], u1 = up[1], d0 = dp[0], d1 = dp[1];
+        rowp[0] = r0.x; rowp[1] = r0.y; rowp[2] = r0.z; rowp[3] = r0.w;
+        rowp[4] = r1.x; rowp[5] = r1.y; rowp[6] = r1.z; rowp[7] = r1.w;
+        u[0] = u0.x; u[1] = u0.y; u[2] = u0.z; u[3] = u0.w; u[4] = u1.x; u[5] = u1.y; u[6] = u1.z; u[7] = u1.w;
+        kde[0] = d0.x; kde[1] = d0.y; kde[2] = d0.z; kde[3] = d0.w;
+        kde[4] = d1.x; kde[5] = d1.y; kde[6] = d1.z; kde[7] = d1.w;
+    }
     float gv[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) gv[t] = __ldg(rowp + kk_of<N>(s, o, jb + t));
+    for (int t = 0; t < 8; ++t) gv[t] = gat<TEX>(G, rowp[t] + ko);
     float key[8];
+    int flat[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-        const float v = s.uv[o][e][jb + t];
-        const float d = ((gv[t] - u) - v) + w;
-        key[t] = fmaf(2.0f, d, ke.x + s.out1[o][jb + t].x);
+        const float d = ((gv[t] - u[t]) - v) + w;
+        key[t] = fmaf(2.0f, d, kde[t] + kdo);
+        flat[t] = (ib + t) * 16 + j;
     }
     if constexpr (FINAL) {
-        const int flat = select_best(key, lane);
+        const int fl = select_best(key, flat, lane);
         if (lane == 0) {
-            const int ne = kk_of<N>(s, e, flat >> 4), no = kk_of<N>(s, o, flat & 15);
+            const int ne = s.kk[e][fl >> 4], no = s.kk[o][fl & 15];
             s.old[e] = ne;
             s.old[o] = no;
         }
         __syncwarp();
     } else {
-        select_sorted<N, 16>(s, key, lane);
+        select_sorted<N, 16>(s, key, flat, lane);
         if (lane < 16) {
             const float2 r = s.sel[lane];
-            const int flat = __float_as_int(r.y);
+            const int fl = __float_as_int(r.y);
             s.kd2[g][lane] = r.x;
-            s.kt2[g][lane] = (unsigned)(flat >> 4) | ((unsigned)(flat & 15) << 4);
+            s.kt2[g][lane] = (unsigned)(fl >> 4) | ((unsigned)(fl & 15) << 4);
         }
         __syncwarp();
     }
 }
 
 // Merge of two codebook pairs: groups e = 2g (codebooks 4g, 4g+1) and o = 2g+1 (4g+2, 4g+3), 16 x 16 candidates.
-template <int N, bool FINAL>
-__device__ __forceinline__ void merge2(WarpMem2<N> &s, const float *__restrict__ G, int g, int lane) {
-    constexpr int NK = N * K2;
+// Same lane mapping as merge1: lane (hi, j) scores (i = 8*hi + t, j).
+template <int N, bool TEX, bool FINAL>
+__device__ __forceinline__ void merge2(WarpMem2<N> &s, const GSrc &G, int g, int lane) {
     const int e = 2 * g, o = e + 1;
     const int a0 = 4 * g, a1 = a0 + 1, b0 = a0 + 2, b1 = a0 + 3;
-    const int i = lane >> 1, jb = (lane & 1) * 8;
-    const unsigned ti = s.kt2[e][i];
-    const int ia0 = ti & 15, ia1 = ti >> 4;
-    const float kde = s.kd2[e][i];
-    const float *rp0 = G + (size_t)(a0 * K2 + kk_of<N>(s, a0, ia0)) * NK;
-    const float *rp1 = G + (size_t)(a1 * K2 + kk_of<N>(s, a1, ia1)) * NK;
-    const float u00 = s.uv[a0][b0][ia0], u10 = s.uv[a1][b0][ia1], u01 = s.uv[a0][b1][ia0], u11 = s.uv[a1][b1][ia1];
-    const float *ro0 = G + (size_t)(a0 * K2 + s.old[a0]) * NK;
-    const float *ro1 = G + (size_t)(a1 * K2 + s.old[a1]) * NK;
-    const int cb0 = b0 * K2 + s.old[b0], cb1 = b1 * K2 + s.old[b1];
-    const float w00 = __ldg(ro0 + cb0), w10 = __ldg(ro1 + cb0), w01 = __ldg(ro0 + cb1), w11 = __ldg(ro1 + cb1);
+    const int j = lane & 15, ib = (lane >> 4) * 8;
+    const unsigned tj = s.kt2[o][j];
+    const int q0 = tj & 15, q1 = tj >> 4;
+    const unsigned c0 = b0 * K2 + s.kk[b0][q0], c1 = b1 * K2 + s.kk[b1][q1];
+    const float v00 = s.uv[b0][a0][q0], v10 = s.uv[b0][a1][q0], v01 = s.uv[b1][a0][q1], v11 = s.uv[b1][a1][q1];
+    const float kdo = s.kd2[o][j];
+    const unsigned cb0 = b0 * K2 + s.old[b0], cb1 = b1 * K2 + s.old[b1];
+    const float w00 = gat<TEX>(G, s.rowoff[a0] + cb0), w10 = gat<TEX>(G, s.rowoff[a1] + cb0);
+    const float w01 = gat<TEX>(G, s.rowoff[a0] + cb1), w11 = gat<TEX>(G, s.rowoff[a1] + cb1);
+    unsigned tis[8];
+    float kde[8];
+    {
+        const uint4 *tp = reinterpret_cast<const uint4 *>(&s.kt2[e][ib]);
+        const float4 *dp = reinterpret_cast<const float4 *>(&s.kd2[e][ib]);
+        const uint4 t0 = tp[0], t1 = tp[1];
+        const float4 d0 = dp[0], d1 = dp[1];
+        tis[0] = t0.x; tis[1] = t0.y; tis[2] = t0.z; tis[3] = t0.w; tis[4] = t1.x; tis[5] = t1.y; tis[6] = t1.z; tis[7] = t1.w;
+        kde[0] = d0.x; kde[1] = d0.y; kde[2] = d0.z; kde[3] = d0.w;
+        kde[4] = d1.x; kde[5] = d1.y; kde[6] = d1.z; kde[7] = d1.w;
+    }
     float g00[8], g10[8], g01[8], g11[8];
-    unsigned tjs[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-        const unsigned tj = s.kt2[o][jb + t];
-        tjs[t] = tj;
-        const int c0 = b0 * K2 + kk_of<N>(s, b0, tj & 15), c1 = b1 * K2 + kk_of<N>(s, b1, tj >> 4);
-        g00[t] = __ldg(rp0 + c0);
-        g10[t] = __ldg(rp1 + c0);
-        g01[t] = __ldg(rp0 + c1);
-        g11[t] = __ldg(rp1 + c1);
+        const unsigned rp0 = s.rowk[a0][tis[t] & 15], rp1 = s.rowk[a1][tis[t] >> 4];
+        g00[t] = gat<TEX>(G, rp0 + c0);
+        g10[t] = gat<TEX>(G, rp1 + c0);
+        g01[t] = gat<TEX>(G, rp0 + c1);
+        g11[t] = gat<TEX>(G, rp1 + c1);
     }
     float key[8];
+    int flat[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-        const int q0 = tjs[t] & 15, q1 = tjs[t] >> 4;
-        const float d00 = ((g00[t] - u00) - s.uv[b0][a0][q0]) + w00;
-        const float d10 = ((g10[t] - u10) - s.uv[b0][a1][q0]) + w10;
-        const float d01 = ((g01[t] - u01) - s.uv[b1][a0][q1]) + w01;
-        const float d11 = ((g11[t] - u11) - s.uv[b1][a1][q1]) + w11;
+        const int ia0 = tis[t] & 15, ia1 = tis[t] >> 4;
+        const float d00 = ((g00[t] - s.uv[a0][b0][ia0]) - v00) + w00;
+        const float d10 = ((g10[t] - s.uv[a1][b0][ia1]) - v10) + w10;
+        const float d01 = ((g01[t] - s.uv[a0][b1][ia0]) - v01) + w01;
+        const float d11 = ((g11[t] - s.uv[a1][b1][ia1]) - v11) + w11;
         const float wb0 = d00 + d10, wb1 = d01 + d11;  // inner sums over a, then b ascending
         const float dot = wb0 + wb1;
-        key[t] = fmaf(2.0f, dot, kde + s.kd2[o][jb + t]);
+        key[t] = fmaf(2.0f, dot, kde[t] + kdo);
+        flat[t] = (ib + t) * 16 + j;
     }
     if constexpr (FINAL) {
-        const int flat = select_best(key, lane);
+        const int fl = select_best(key, flat, lane);
         if (lane == 0) {
-            const unsigned te = s.kt2[e][flat >> 4], to = s.kt2[o][flat & 15];
-            const int n0 = kk_of<N>(s, a0, te & 15), n1 = kk_of<N>(s, a1, te >> 4);
-            const int n2 = kk_of<N>(s, b0, to & 15), n3 = kk_of<N>(s, b1, to >> 4);
+            const unsigned te = s.kt2[e][fl >> 4], to = s.kt2[o][fl & 15];
+            const int n0 = s.kk[a0][te & 15], n1 = s.kk[a1][te >> 4];
+            const int n2 = s.kk[b0][to & 15], n3 = s.kk[b1][to >> 4];
             s.old[a0] = n0;
             s.old[a1] = n1;
             s.old[b0] = n2;
@@ -266,21 +328,20 @@ __device__ __forceinline__ void merge2(WarpMem2<N> &s, const float *__restrict__
         }
         __syncwarp();
     } else {
-        select_sorted<N, 32>(s, key, lane);
+        select_sorted<N, 32>(s, key, flat, lane);
         {
             const float2 r = s.sel[lane];
-            const int flat = __float_as_int(r.y);
+            const int fl = __float_as_int(r.y);
             s.kd3[g][lane] = r.x;
-            s.kt3[g][lane] = s.kt2[e][flat >> 4] | (s.kt2[o][flat & 15] << 8);
+            s.kt3[g][lane] = s.kt2[e][fl >> 4] | (s.kt2[o][fl & 15] << 8);
         }
         __syncwarp();
     }
 }
 
 // Final merge of two codebook quads (N = 8): 32 x 32 joint candidates, candidate flat = i*32 + j.
-template <int N>
-__device__ __forceinline__ void merge4_final(WarpMem2<N> &s, const float *__restrict__ G, int lane) {
-    constexpr int NK = N * K2;
+template <int N, bool TEX>
+__device__ __forceinline__ void merge4_final(WarpMem2<N> &s, const GSrc &G, int lane) {
     const unsigned ti = s.kt3[0][lane];  // as row i = lane: my slots of codebooks 0..3
     const unsigned tj = s.kt3[1][lane];  // as column j = lane: my slots of codebooks 4..7
 #pragma unroll
@@ -296,54 +357,60 @@ __device__ __forceinline__ void merge4_final(WarpMem2<N> &s, const float *__rest
     float dot[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) dot[i] = 0.0f;
-    float(*es)[16] = reinterpret_cast<float(*)[16]>(&s.lists[0][0]);
-    const int p = lane >> 1, qb = (lane & 1) * 8;
+    // table T_ab: lane (hi, q) computes rows p = 8*hi + t of column q -- a request reads two G rows x 16 columns
+    const int q = lane & 15, pb = (lane >> 4) * 8;
 #pragma unroll 1
     for (int lb = 0; lb < 4; ++lb) {
         const int b = 4 + lb;
-        const unsigned ub = s.used[4 + lb];
+        const unsigned cq = b * K2 + s.kk[b][q];
+        const bool colu = (s.used[4 + lb] >> q) & 1u;  // does any candidate still use slot q of codebook b?
+        const unsigned cbo = b * K2 + s.old[b];
         float E[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) E[q] = 0.0f;
+        for (int c = 0; c < 16; ++c) E[c] = 0.0f;
 #pragma unroll 1
         for (int a = 0; a < 4; ++a) {
-            const bool rowu = (s.used[a] >> p) & 1u;
-            const float *rowp = G + (size_t)(a * K2 + kk_of<N>(s, a, p)) * NK + b * K2;
-            const float u = s.uv[a][b][p];
-            const float w = __ldg(G + (size_t)(a * K2 + s.old[a]) * NK + b * K2 + s.old[b]);
+            const unsigned msk = colu ? (s.used[a] >> pb) & 0xffu : 0u;  // rows of my half that are still in use
+            unsigned ra[8];
+            float u[8];
+            {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(&s.rowk[a][pb]);
+                const float4 *up = reinterpret_cast<const float4 *>(&s.uv[a][b][pb]);
+                const uint4 r0 = rp[0], r1 = rp[1];
+                const float4 u0 = up[0], u1 = up[1];
+                ra[0] = r0.x; ra[1] = r0.y; ra[2] = r0.z; ra[3] = r0.w; ra[4] = r1.x; ra[5] = r1.y; ra[6] = r1.z; ra[7] = r1.w;
+                u[0] = u0.x; u[1] = u0.y; u[2] = u0.z; u[3] = u0.w; u[4] = u1.x; u[5] = u1.y; u[6] = u1.z; u[7] = u1.w;
+            }
             float gv[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 gv[t] = 0.0f;
-                if (rowu && ((ub >> (qb + t)) & 1u)) gv[t] = __ldg(rowp + kk_of<N>(s, b, qb + t));
+                if ((msk >> t) & 1u) gv[t] = gat<TEX>(G, ra[t] + cq);
             }
-            float d[8];
+            const float v = s.uv[b][a][q];
+            const float w = gat<TEX>(G, s.rowoff[a] + cbo);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) d[t] = ((gv[t] - u) - s.uv[b][a][qb + t]) + w;
-            float4 *trow = reinterpret_cast<float4 *>(&s.tab[p][qb]);
-            trow[0] = make_float4(d[0], d[1], d[2], d[3]);
-            trow[1] = make_float4(d[4], d[5], d[6], d[7]);
+            for (int t = 0; t < 8; ++t) s.tab[trow_off(pb + t) + q] = ((gv[t] - u[t]) - v) + w;
             __syncwarp();
-            const float4 *mine = reinterpret_cast<const float4 *>(&s.tab[(ti >> (4 * a)) & 15][0]);
+            const float4 *mine = reinterpret_cast<const float4 *>(&s.tab[trow_off((ti >> (4 * a)) & 15)]);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const float4 r = mine[c];
-                E[4 * c + 0] = E[4 * c + 0] + r.x;
-                E[4 * c + 1] = E[4 * c + 1] + r.y;
-                E[4 * c + 2] = E[4 * c + 2] + r.z;
-                E[4 * c + 3] = E[4 * c + 3] + r.w;
+                fadd2(E[4 * c + 0], E[4 * c + 1], r.x, r.y);
+                fadd2(E[4 * c + 2], E[4 * c + 3], r.z, r.w);
             }
             __syncwarp();
         }
-        float4 *erow = reinterpret_cast<float4 *>(&es[lane][0]);
+        float4 *erow = reinterpret_cast<float4 *>(&s.es[lane][0]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) erow[c] = make_float4(E[4 * c], E[4 * c + 1], E[4 * c + 2], E[4 * c + 3]);
         __syncwarp();
         const int jq = (tj >> (4 * lb)) & 15;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) dot[i] = dot[i] + es[i][jq];
+        for (int i = 0; i < 32; ++i) dot[i] = dot[i] + s.es[i][jq];
         __syncwarp();
     }
+    s.lists[8][lane] = make_float2(__int_as_float(0x7f800000), __int_as_float(0));  // es overwrote the sentinels
     const float kdo = s.kd3[1][lane];
     float best = fmaf(2.0f, dot[0], s.kd3[0][0] + kdo);
     int bi = 0;
@@ -362,27 +429,28 @@ __device__ __forceinline__ void merge4_final(WarpMem2<N> &s, const float *__rest
     const unsigned te = s.kt3[0][flat >> 5], to = s.kt3[1][flat & 31];
     if (lane < 8) {
         const unsigned tt = lane < 4 ? te : to;
-        s.old[lane] = kk_of<N>(s, lane, (tt >> (4 * (lane & 3))) & 15);
+        s.old[lane] = s.kk[lane][(tt >> (4 * (lane & 3))) & 15];
     }
     __syncwarp();
 }
 
-template <int N>
-__device__ __forceinline__ void refine_pass2(WarpMem2<N> &s, const float *__restrict__ Pb,
-                                             const float *__restrict__ G, int lane) {
-    level1<N>(s, Pb, G, lane);
-    gather_uv<N>(s, G, lane);
+template <int N, bool TEX>
+__device__ __forceinline__ void refine_pass2(WarpMem2<N> &s, const float *__restrict__ Pb, const GSrc &G, int lane) {
+    if (lane < N) s.rowoff[lane] = (unsigned)(lane * K2 + s.old[lane]) * (unsigned)(N * K2);
+    __syncwarp();
+    level1<N>(s, Pb, G.g, lane);
+    gather_uv<N, TEX>(s, G, lane);
     if constexpr (N == 2) {
-        merge1<N, true>(s, G, 0, lane);
+        merge1<N, TEX, true>(s, G, 0, lane);
     } else {
 #pragma unroll 1
-        for (int g = 0; g < N / 2; ++g) merge1<N, false>(s, G, g, lane);
+        for (int g = 0; g < N / 2; ++g) merge1<N, TEX, false>(s, G, g, lane);
         if constexpr (N == 4) {
-            merge2<N, true>(s, G, 0, lane);
+            merge2<N, TEX, true>(s, G, 0, lane);
         } else {
 #pragma unroll 1
-            for (int g = 0; g < N / 4; ++g) merge2<N, false>(s, G, g, lane);
-            merge4_final<N>(s, G, lane);
+            for (int g = 0; g < N / 4; ++g) merge2<N, TEX, false>(s, G, g, lane);
+            merge4_final<N, TEX>(s, G, lane);
         }
     }
 }
@@ -392,10 +460,10 @@ struct Launch2 {
     static constexpr int WPC = (N == 8) ? 5 : 8;  // warps per CTA
 };
 
-template <int N>
+template <int N, bool TEX>
 __global__ void __launch_bounds__(Launch2<N>::WPC * 32, (N == 8 ? 4 : 3))
-    search2_kernel(const float *__restrict__ P, const float *__restrict__ G, int64_t B, int iters,
-                   const int32_t *__restrict__ idx_in, int32_t *__restrict__ idx_out) {
+    search2_kernel(const float *__restrict__ P, GSrc G, int64_t B, int iters, const int32_t *__restrict__ idx_in,
+                   int32_t *__restrict__ idx_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int wpc = Launch2<N>::WPC;
@@ -410,7 +478,7 @@ __global__ void __launch_bounds__(Launch2<N>::WPC * 32, (N == 8 ? 4 : 3))
 #pragma unroll 1
         for (int it = 0; it < iters; ++it) {
             const int prev = (lane < N) ? s.old[lane] : 0;
-            refine_pass2<N>(s, Pb, G, lane);
+            refine_pass2<N, TEX>(s, Pb, G, lane);
             const int now = (lane < N) ? s.old[lane] : 0;
             // a pass that returns its input is a fixed point of a deterministic map: the remaining passes are no-ops
             if (__all_sync(FULL, prev == now)) break;
@@ -420,12 +488,12 @@ __global__ void __launch_bounds__(Launch2<N>::WPC * 32, (N == 8 ? 4 : 3))
     }
 }
 
-template <int N>
-int launch2(const float *P, const float *G, int64_t B, int iters, const int32_t *idx_in, int32_t *idx_out,
-            cudaStream_t st) {
+template <int N, bool TEX>
+int launch2t(const float *P, const GSrc &G, int64_t B, int iters, const int32_t *idx_in, int32_t *idx_out,
+             cudaStream_t st) {
     constexpr int wpc = Launch2<N>::WPC;
     const size_t smem = sizeof(WarpMem2<N>) * wpc;
-    auto kern = search2_kernel<N>;
+    auto kern = search2_kernel<N, TEX>;
     MCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     MCQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
@@ -440,6 +508,13 @@ int launch2(const float *P, const float *G, int64_t B, int iters, const int32_t 
     kern<<<(unsigned)grid, wpc * 32, smem, st>>>(P, G, B, iters, idx_in, idx_out);
     MCQ_LAUNCH_CHECK("search2_kernel");
     return MCQ_OK;
+}
+
+template <int N>
+int launch2(const float *P, const float *Gp, int64_t B, int iters, const int32_t *idx_in, int32_t *idx_out,
+            cudaStream_t st) {
+    GSrc G{Gp};
+    return launch2t<N, false>(P, G, B, iters, idx_in, idx_out, st);
 }
 
 }  // namespace

@@ -31,8 +31,9 @@ ws = q._workspace(B)
 _lib.check(L.mcq_xct(x.data_ptr(), 0, B, D, N, K, base, P.data_ptr(), ws.data_ptr(), ws.numel(),
                      _lib.stream_ptr(dev)), "xct")
 idx0 = q.encode(x, refine_indexes_iters=0, as_bytes=False).to(torch.int32).contiguous()
+VERS = tuple(os.environ.get("MCQ_ONLY", "v1,v2").split(","))
 res = {}
-for ver in ("v1", "v2"):
+for ver in VERS:
     os.environ["MCQ_SEARCH"] = ver
     out = torch.empty_like(idx0)
     for it in range(2):
@@ -50,10 +51,10 @@ for ver in ("v1", "v2"):
     ms = e0.elapsed_time(e1) / reps
     res[ver] = out.clone()
     print(f"{ver}: {ms:.3f} ms per launch of {B} frames (N={N}) -> {B / ms / 1e3:.2f} Mvec/s search-only", flush=True)
-bad = int((res["v1"] != res["v2"]).any(1).sum())
+bad = int((res[VERS[0]] != res[VERS[-1]]).any(1).sum())
 print(f"v1 vs v2: {bad}/{B} frames differ")
 # one-pass variant (pass count 1) to get time per pass
-for ver in ("v1", "v2"):
+for ver in VERS:
     os.environ["MCQ_SEARCH"] = ver
     out = torch.empty_like(idx0)
     L.mcq_search(P.data_ptr(), g_ptr, B, N, K, 1, idx0.data_ptr(), out.data_ptr(), _lib.stream_ptr(dev))
