@@ -107,7 +107,7 @@ __device__ __forceinline__ void select_sorted(WarpMem2<N> &s, const float (&key)
     for (int t = 0; t < 8; ++t) s.lists[rank[t]][lane] = make_float2(key[t], __int_as_float(flat[t]));
     // a lane reads back only its own column: no warp synchronisation needed here
     const float2 *col = &s.lists[0][lane];
-    float2 head = col[0];
+    float2 head = col[0], nxt = col[32];  // the successor is fetched ahead so that a pop does not wait on shared memory
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const float m = credux_min(head.x);
@@ -116,8 +116,9 @@ __device__ __forceinline__ void select_sorted(WarpMem2<N> &s, const float (&key)
         const bool mine = (f == __reduce_min_sync(FULL, f)) && f != 0x7fffffffu;
         if (mine) {
             s.sel[r] = head;
+            head = nxt;
             col += 32;
-            head = *col;
+            nxt = col[32];  // at most row 9: inside the union (es) even after the sentinel row
         }
     }
     __syncwarp();
@@ -146,7 +147,6 @@ __device__ __forceinline__ void level1(WarpMem2<N> &s, const float *__restrict__
                                        int lane) {
     constexpr unsigned NK = N * K2;
     const float *diag = Gp + (size_t)NK * NK;
-    float *scratch = &s.tab[0];
     int flat[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) flat[t] = (t < 4 ? 0 : 128 - 4) + lane * 4 + t;
@@ -178,10 +178,13 @@ __device__ __forceinline__ void level1(WarpMem2<N> &s, const float *__restrict__
         v[5] = fmaf(2.0f, acc[5] - p1.y, d1.y);
         v[6] = fmaf(2.0f, acc[6] - p1.z, d1.z);
         v[7] = fmaf(2.0f, acc[7] - p1.w, d1.w);
-        reinterpret_cast<float4 *>(scratch)[lane] = make_float4(v[0], v[1], v[2], v[3]);
-        reinterpret_cast<float4 *>(scratch)[32 + lane] = make_float4(v[4], v[5], v[6], v[7]);
-        __syncwarp();
-        const float vold = scratch[s.old[n]];
+        // v of the current entry old[n]: it lives in lane (old >> 2) & 31 as element (old & 3) + 4 * (old >= 128)
+        const int on = s.old[n];
+        const int tsel = (on & 3) | ((on >> 5) & 4);
+        float vs = v[0];
+#pragma unroll
+        for (int t = 1; t < 8; ++t) vs = (tsel == t) ? v[t] : vs;
+        const float vold = __shfl_sync(FULL, vs, (on >> 2) & 31);
         float key[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) key[t] = v[t] - vold;
@@ -199,14 +202,23 @@ __device__ __forceinline__ void level1(WarpMem2<N> &s, const float *__restrict__
 template <int N, bool TEX>
 __device__ __forceinline__ void gather_uv(WarpMem2<N> &s, const GSrc &G, int lane) {
     const int p = lane & 15, mh = lane >> 4;
-#pragma unroll 1
-    for (int a = 0; a < N; ++a) {
-        const unsigned col = a * K2 + s.kk[a][p];
+    unsigned ro[N / 2];
 #pragma unroll
-        for (int r = 0; r < N / 2; ++r) {
-            const int m = 2 * r + mh;
-            if (m != a) s.uv[a][m][p] = gat<TEX>(G, s.rowoff[m] + col);
+    for (int r = 0; r < N / 2; ++r) ro[r] = s.rowoff[2 * r + mh];
+    constexpr int AB = (N >= 4) ? 4 : N;  // codebooks per batch: AB * N/2 loads in flight per lane
+#pragma unroll 1
+    for (int a0 = 0; a0 < N; a0 += AB) {
+        float val[AB][N / 2];
+#pragma unroll
+        for (int aa = 0; aa < AB; ++aa) {
+            const unsigned col = (a0 + aa) * K2 + s.kk[a0 + aa][p];
+#pragma unroll
+            for (int r = 0; r < N / 2; ++r) val[aa][r] = gat<TEX>(G, ro[r] + col);  // (m == a is read but not used)
         }
+#pragma unroll
+        for (int aa = 0; aa < AB; ++aa)
+#pragma unroll
+            for (int r = 0; r < N / 2; ++r) s.uv[a0 + aa][2 * r + mh][p] = val[aa][r];
     }
     __syncwarp();
 }
