@@ -251,7 +251,7 @@ def run_ours(args, rank, world, local_rank):
     search_avg_ms = s_ms / max(s_n, 1)
     flop_search = (FLOP_PER_FRAME_TOTAL - FLOP_PER_FRAME_INIT) * frames_per_launch
     achieved_tf = flop_search / (search_avg_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "search_kernel<256,8>", "achieved": achieved_tf, "peak": peaks["tf_sust"],
+    roofline = {"bound": "tensor", "kernel": "search2_kernel<8> (search.cu generic kernel for other shapes)", "achieved": achieved_tf, "peak": peaks["tf_sust"],
                 "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf_sust"], "traffic": load_traffic(),
                 "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({peaks['src']})",
                 "algorithmic_flop_per_frame": FLOP_PER_FRAME_TOTAL - FLOP_PER_FRAME_INIT,
