@@ -119,6 +119,51 @@ def cpu_port_run(x_np, params, threads=0):
     return time.perf_counter() - t0, idx
 
 
+def reference_gpu_leg(x_host, params, dev, frames=65536):
+    """The UNMODIFIED reference (pip-installed into the git-ignored baseline/_ref) on the same GPU:
+    its own Quantizer.encode, fp32, TF32 off (PyTorch default), torch.no_grad(), one 65,536-frame chunk (its
+    (B, N, 16, dim) fp32 temporaries do not allow the full 2^20-frame batch).  Informational: the denominator of
+    north_star's "10x the reference GPU PyTorch path".  Returns None when baseline/_ref is not there."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "quantization")):
+        return None
+    import types
+
+    import torch
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))  # the reference imports h5py only for read_hdf5_data
+    sys.path.insert(0, ref_dir)
+    try:
+        import quantization as refq
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": f"import failed: {e}"}
+    finally:
+        sys.path.remove(ref_dir)
+    q = refq.Quantizer(dim=DIM, codebook_size=KSZ, num_codebooks=NCB)
+    with torch.no_grad():
+        q.centers.copy_(params["centers"])
+        q.to_logits.weight.copy_(params["weight"])
+        q.to_logits.bias.copy_(params["bias"])
+    q = q.to(dev)
+    x = x_host[:frames].to(dev)
+    sub = 16384  # keeps the reference's temporaries (256 KiB per frame, several live copies) well inside HBM
+    with torch.no_grad():
+        def enc():
+            return torch.cat([q.encode(x[i:i + sub], refine_indexes_iters=ITERS) for i in range(0, frames, sub)])
+        codes = enc()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reps = 2
+        for _ in range(reps):
+            codes = enc()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"value": frames / (ms * 1e-3) / 1e6, "unit": UNIT, "frames": frames, "ms": ms,
+            "how": "reference Quantizer.encode from baseline/_ref on cuda, fp32, no_grad, 16,384-frame sub-batches",
+            "codes": codes}
+
+
 def run_reference(args, rank, world):
     """The reference arm: the reference's algorithm on the host cores (CPU port in oracle/, all threads)."""
     if rank != 0:
@@ -309,6 +354,17 @@ def run_ours(args, rank, world, local_rank):
         line["cpu_baseline"] = {"value": CPU_SAMPLE / sec / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{CPU_SAMPLE}-frame prefix of the batch, one pass of oracle/mcq_oracle.c "
                                           "(OpenMP, all host threads)"}
+        try:
+            rg = reference_gpu_leg(x_host, params, dev)
+        except Exception as e:  # the reference's own failure must not take the bench line down
+            rg = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        if rg is not None:
+            rc = rg.pop("codes", None)
+            if rc is not None:
+                n = rc.shape[0]
+                rg["frames_with_different_codes_vs_ours"] = int((rc != codes[:n]).any(1).sum().item())
+                rg["speedup_of_value_over_reference_gpu"] = value / rg["value"]
+            line["reference_gpu_pytorch"] = rg
         line["parity"] = {"sample_frames": CPU_SAMPLE,
                           "frames_with_different_codes": int((ours != ref_idx).any(1).sum()),
                           "rel_reconstruction_mse_ours": rel_err(ours), "rel_reconstruction_mse_ref": rel_err(ref_idx)}

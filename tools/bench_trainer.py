@@ -1,0 +1,55 @@
+#!/usr/bin/env python3
+"""QuantizerTrainer.step timing at BASELINE configs[2]: dim=256, bytes_per_frame=4, batch=65536 bf16.
+    python tools/bench_trainer.py [steps_per_phase] [batch]
+Times `steps` steps in phase 1 (K=16, N=8) and in phase 2 (K=256, N=4) with CUDA events, and prints where a step's
+GPU time goes (library kernels by kind via mcq_profile, the rest = PyTorch loss/backward/Adam)."""
+import os
+import random
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+from quantization_b200 import QuantizerTrainer, _lib, synth
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+D = 256
+dev = torch.device("cuda:0")
+torch.manual_seed(1)
+random.seed(1)
+x = synth.synth_x(B, D, 1234 + 2, torch.bfloat16).to(dev)
+
+
+def run(tr, tag):
+    for _ in range(3):
+        tr.step(x)
+    torch.cuda.synchronize()
+    _lib.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        tr.step(x)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / steps * 1e3
+    ms = e0.elapsed_time(e1) / steps
+    prof = _lib.profile_read()
+    _lib.profile(False)
+    parts = {k: round(v[0] / steps, 3) for k, v in prof.items()}
+    q = tr.quantizer
+    print(f"{tag}: K={q.codebook_size} N={q.num_codebooks} B={B}: {ms:.2f} ms/step (wall {wall:.2f}), "
+          f"library kernels ms/step {parts} -> {B / ms / 1e3:.2f} Mframes/s; 20,001 steps = {ms * 20001 / 1e3:.0f} s",
+          flush=True)
+
+
+tr = QuantizerTrainer(dim=D, bytes_per_frame=4, device=dev, phase_one_iters=10000, phase_two_iters=10000)
+tr.cur_iter = 1  # stay clear of the every-200-iterations diagnostics
+run(tr, "phase 1")
+tr.cur_iter = tr.phase_one_iters
+tr.step(x)  # switches to phase 2 (get_product_quantizer)
+tr.cur_iter = tr.phase_one_iters + 2
+run(tr, "phase 2")
