@@ -191,7 +191,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -369,12 +369,31 @@ def run_ours(args, rank, world, local_rank):
                           "frames_with_different_codes": int((ours != ref_idx).any(1).sum()),
                           "rel_reconstruction_mse_ours": rel_err(ours), "rel_reconstruction_mse_ref": rel_err(ref_idx)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _route_stdout_to_stderr():
+    """Everything libraries write to fd 1 (e.g. NCCL's "NCCL version ..." banner) goes to stderr, so that stdout
+    carries exactly the one JSON line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _route_stdout_to_stderr()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
