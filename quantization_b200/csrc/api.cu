@@ -73,6 +73,7 @@ Workspace workspace_layout(int64_t Bc, int N, int K, int D) {
     W.off_lsplit = take(sizeof(__nv_bfloat16) * 3 * (size_t)W.Mp * Dp);
     W.off_p = take(sizeof(float) * (size_t)W.Mp * NK);
     W.off_idx = take(sizeof(int32_t) * (size_t)W.Mp * N);
+    W.off_ctr = take(1024);
     W.bytes = off;
     return W;
 }
@@ -80,11 +81,24 @@ Workspace workspace_layout(int64_t Bc, int N, int K, int D) {
 // Largest chunk (multiple of 128 frames) whose workspace fits in `bytes`.
 static int64_t chunk_for(size_t bytes, int64_t B, int N, int K, int D) {
     int64_t hi = (int64_t)align_up((size_t)(B > 0 ? B : 1), 128);
-    const int64_t cap = 148 * 128 * 4;  // 75,776 frames: four full waves of 128-frame GEMM tiles
+    const int64_t cap = max_chunk_frames();
     if (hi > cap) hi = cap;
     while (hi > 128 && workspace_layout(hi, N, K, D).bytes > bytes) hi -= 128;
     if (workspace_layout(hi, N, K, D).bytes > bytes) return 0;
     return hi;
+}
+
+// Frames per chunk of mcq_encode / mcq_refine: a multiple of 148 x 128 (full waves of 128-frame GEMM tiles).
+// MCQ_CHUNK_WAVES overrides the number of waves (measurements only).
+int64_t max_chunk_frames() {
+    static int64_t cap = 0;
+    if (cap == 0) {
+        int waves = 4;
+        const char *e = getenv("MCQ_CHUNK_WAVES");
+        if (e && atoi(e) > 0) waves = atoi(e);
+        cap = (int64_t)148 * 128 * waves;
+    }
+    return cap;
 }
 
 // MCQ_GEMM=ffma routes the two GEMMs through the CUDA-core kernel (used by the tests to cross-check tcgen05).
@@ -195,7 +209,7 @@ size_t mcq_prepared_bytes(int N, int K, int D) {
 size_t mcq_workspace_bytes(int64_t max_frames, int D, int N, int K) {
     if (check_shape(N, K, D)) return 0;
     if (max_frames < 1) max_frames = 1;
-    int64_t cap = 148 * 128 * 4;
+    int64_t cap = max_chunk_frames();
     int64_t Bc = (int64_t)align_up((size_t)max_frames, 128);
     if (Bc > cap) Bc = cap;
     return workspace_layout(Bc, N, K, D).bytes;
@@ -270,8 +284,10 @@ int mcq_encode(const void *x, int x_dtype, int64_t B, int D, int N, int K, const
             return rc;
         if (iters > 0) {
             if ((rc = PROF(MCQ_PROF_GEMM, st, chunk_gemm(L, blob, W, ws, false, nb, st)))) return rc;
+            unsigned *ctr = (unsigned *)(ws + W.off_ctr);
+            MCQ_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned), st));
             if ((rc = PROF(MCQ_PROF_SEARCH, st,
-                           launch_search(P, (const float *)(blob + L.off_gram), nb, N, K, iters, idx, idx, st))))
+                           launch_search(P, (const float *)(blob + L.off_gram), nb, N, K, iters, idx, idx, st, ctr))))
                 return rc;
         }
         if ((rc = PROF(MCQ_PROF_OTHER, st,
@@ -313,8 +329,10 @@ int mcq_refine(const void *x, int x_dtype, int64_t B, int D, int N, int K, const
         if (iters > 0) {
             if ((rc = PROF(MCQ_PROF_OTHER, st, launch_split_x(xc, x_dtype, nb, L, blob, W, ws, false, st)))) return rc;
             if ((rc = PROF(MCQ_PROF_GEMM, st, chunk_gemm(L, blob, W, ws, false, nb, st)))) return rc;
+            unsigned *ctr = (unsigned *)(ws + W.off_ctr);
+            MCQ_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned), st));
             if ((rc = PROF(MCQ_PROF_SEARCH, st,
-                           launch_search(P, (const float *)(blob + L.off_gram), nb, N, K, iters, idx, idx, st))))
+                           launch_search(P, (const float *)(blob + L.off_gram), nb, N, K, iters, idx, idx, st, ctr))))
                 return rc;
         }
         if ((rc = PROF(MCQ_PROF_OTHER, st, launch_i32_to_i64(idx, idx_out + (size_t)b0 * N, nb * N, st)))) return rc;

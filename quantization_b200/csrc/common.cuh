@@ -53,6 +53,7 @@ struct Workspace {
     size_t off_lsplit; // bf16  [3][Mp*Dp]  split of fl(logits_scale * x)
     size_t off_p;      // float [Mp*NK]     P = x Cs^T   (also receives the logits before P is formed)
     size_t off_idx;    // int32 [Mp*N]
+    size_t off_ctr;    // uint32 [256]      work counter of the search kernel (dynamic frame scheduling)
     size_t bytes;
 };
 
@@ -73,12 +74,15 @@ int launch_gemm_ffma(const float *A, const float *Bm, float *C, int64_t M, int N
 int launch_gemm_tc(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, float *C, int64_t Mp, int NK, int Dp,
                    cudaStream_t st);
 int launch_argmax_init(const float *logits, const float *bias, int64_t B, int N, int K, int32_t *idx, cudaStream_t st);
+// work_counter (optional, device, zeroed by the caller on `st`): lets the warps of the search kernel fetch frames
+// dynamically instead of striding over the batch (frames take 2..iters passes, so static striding leaves a tail)
 int launch_search(const float *P, const float *gram, int64_t B, int N, int K, int iters, const int32_t *idx_in,
-                  int32_t *idx_out, cudaStream_t st);
+                  int32_t *idx_out, cudaStream_t st, unsigned *work_counter = nullptr);
 // second version of the search (search2.cu): codebook_size 256, 2/4/8 codebooks
 bool search2_supports(int N, int K);
 int launch_search2(const float *P, const float *gram, int64_t B, int N, int K, int iters, const int32_t *idx_in,
-                   int32_t *idx_out, cudaStream_t st);
+                   int32_t *idx_out, cudaStream_t st, unsigned *work_counter);
+int64_t max_chunk_frames();
 int launch_pack(const int32_t *idx, int64_t B, int N, int K, void *codes, int codes_dtype, cudaStream_t st);
 int launch_i64_to_i32(const int64_t *src, int32_t *dst, int64_t n, int K, cudaStream_t st);
 int launch_i32_to_i64(const int32_t *src, int64_t *dst, int64_t n, cudaStream_t st);

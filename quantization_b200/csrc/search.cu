@@ -386,13 +386,13 @@ int dispatch_n(int N, const float *P, const float *G, int64_t B, int iters, cons
 }  // namespace
 
 int launch_search(const float *P, const float *gram, int64_t B, int N, int K, int iters, const int32_t *idx_in,
-                  int32_t *idx_out, cudaStream_t st) {
+                  int32_t *idx_out, cudaStream_t st, unsigned *work_counter) {
     if (B <= 0) return MCQ_OK;
     {
         // MCQ_SEARCH=v1 keeps the generic first version for every shape (used by the tests to cross-check)
         const char *e = getenv("MCQ_SEARCH");
         const bool force_v1 = e && strcmp(e, "v1") == 0;
-        if (!force_v1 && search2_supports(N, K)) return launch_search2(P, gram, B, N, K, iters, idx_in, idx_out, st);
+        if (!force_v1 && search2_supports(N, K)) return launch_search2(P, gram, B, N, K, iters, idx_in, idx_out, st, work_counter);
     }
     switch (K) {
         case 2: return dispatch_n<2>(N, P, gram, B, iters, idx_in, idx_out, st);

@@ -475,7 +475,7 @@ struct Launch2 {
 template <int N, bool TEX>
 __global__ void __launch_bounds__(Launch2<N>::WPC * 32, (N == 8 ? 4 : 3))
     search2_kernel(const float *__restrict__ P, GSrc G, int64_t B, int iters, const int32_t *__restrict__ idx_in,
-                   int32_t *__restrict__ idx_out) {
+                   int32_t *__restrict__ idx_out, unsigned *__restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int wpc = Launch2<N>::WPC;
@@ -483,7 +483,10 @@ __global__ void __launch_bounds__(Launch2<N>::WPC * 32, (N == 8 ? 4 : 3))
     s.lists[8][lane] = make_float2(__int_as_float(0x7f800000), __int_as_float(0));
     s.sel[lane] = make_float2(0.0f, __int_as_float(0));
     __syncwarp();
-    for (int64_t b = (int64_t)blockIdx.x * wpc + warp; b < B; b += (int64_t)gridDim.x * wpc) {
+    // the first frame of a warp is its global warp index; further frames come from the work counter when there is
+    // one (frames take 2..iters passes, so static striding would leave a tail), else by striding over the batch
+    const int64_t nwarps = (int64_t)gridDim.x * wpc;
+    for (int64_t b = (int64_t)blockIdx.x * wpc + warp; b < B;) {
         if (lane < N) s.old[lane] = idx_in[(size_t)b * N + lane];
         __syncwarp();
         const float *Pb = P + (size_t)b * (N * K2);
@@ -496,13 +499,20 @@ __global__ void __launch_bounds__(Launch2<N>::WPC * 32, (N == 8 ? 4 : 3))
             if (__all_sync(FULL, prev == now)) break;
         }
         if (lane < N) idx_out[(size_t)b * N + lane] = s.old[lane];
+        if (work_counter != nullptr) {
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(work_counter, 1u);
+            b = nwarps + (int64_t)__shfl_sync(FULL, t, 0);
+        } else {
+            b += nwarps;
+        }
         __syncwarp();
     }
 }
 
 template <int N, bool TEX>
 int launch2t(const float *P, const GSrc &G, int64_t B, int iters, const int32_t *idx_in, int32_t *idx_out,
-             cudaStream_t st) {
+             cudaStream_t st, unsigned *work_counter) {
     constexpr int wpc = Launch2<N>::WPC;
     const size_t smem = sizeof(WarpMem2<N>) * wpc;
     auto kern = search2_kernel<N, TEX>;
@@ -517,16 +527,16 @@ int launch2t(const float *P, const GSrc &G, int64_t B, int iters, const int32_t 
     int64_t grid = (int64_t)sms * per_sm;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, wpc * 32, smem, st>>>(P, G, B, iters, idx_in, idx_out);
+    kern<<<(unsigned)grid, wpc * 32, smem, st>>>(P, G, B, iters, idx_in, idx_out, work_counter);
     MCQ_LAUNCH_CHECK("search2_kernel");
     return MCQ_OK;
 }
 
 template <int N>
 int launch2(const float *P, const float *Gp, int64_t B, int iters, const int32_t *idx_in, int32_t *idx_out,
-            cudaStream_t st) {
+            cudaStream_t st, unsigned *work_counter) {
     GSrc G{Gp};
-    return launch2t<N, false>(P, G, B, iters, idx_in, idx_out, st);
+    return launch2t<N, false>(P, G, B, iters, idx_in, idx_out, st, work_counter);
 }
 
 }  // namespace
@@ -534,13 +544,13 @@ int launch2(const float *P, const float *Gp, int64_t B, int iters, const int32_t
 bool search2_supports(int N, int K) { return K == 256 && (N == 2 || N == 4 || N == 8); }
 
 int launch_search2(const float *P, const float *gram, int64_t B, int N, int K, int iters, const int32_t *idx_in,
-                   int32_t *idx_out, cudaStream_t st) {
+                   int32_t *idx_out, cudaStream_t st, unsigned *work_counter) {
     if (B <= 0) return MCQ_OK;
     if (K == 256) {
         switch (N) {
-            case 2: return launch2<2>(P, gram, B, iters, idx_in, idx_out, st);
-            case 4: return launch2<4>(P, gram, B, iters, idx_in, idx_out, st);
-            case 8: return launch2<8>(P, gram, B, iters, idx_in, idx_out, st);
+            case 2: return launch2<2>(P, gram, B, iters, idx_in, idx_out, st, work_counter);
+            case 4: return launch2<4>(P, gram, B, iters, idx_in, idx_out, st, work_counter);
+            case 8: return launch2<8>(P, gram, B, iters, idx_in, idx_out, st, work_counter);
             default: break;
         }
     }
