@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcq.so")
+LIB_PATH = os.environ.get("MCQ_LIB") or os.path.join(_HERE, "libmcq.so")  # MCQ_LIB: A/B builds of the same ABI
 
 F32, F16, BF16 = 0, 1, 2
 U8, I64, I32 = 0, 1, 2

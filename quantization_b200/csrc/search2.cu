@@ -25,6 +25,9 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int K2 = 256;
+#ifndef MCQ_S2_WPC
+#define MCQ_S2_WPC 5
+#endif
 
 __device__ __forceinline__ float credux_min(float v) {
     float m;
@@ -469,7 +472,7 @@ __device__ __forceinline__ void refine_pass2(WarpMem2<N> &s, const float *__rest
 
 template <int N>
 struct Launch2 {
-    static constexpr int WPC = (N == 8) ? 5 : 8;  // warps per CTA
+    static constexpr int WPC = (N == 8) ? MCQ_S2_WPC : 8;  // warps per CTA
 };
 
 template <int N, bool TEX>
