@@ -120,6 +120,48 @@ def test_search_bit_exact_vs_model(golden_cases, name):
     assert nbad == 0, f"{nbad}/{len(ref)} frames differ from the bit-level model"
 
 
+@pytest.mark.parametrize("N,D,B", [(8, 512, 20000), (4, 256, 12000), (2, 128, 6000)])
+@pytest.mark.parametrize("quantised", [False, True])
+def test_search_versions_agree(N, D, B, quantised):
+    """The generic first-version kernel (MCQ_SEARCH=v1) and the K=256 kernel (search2.cu) are two implementations of
+    one arithmetic contract: identical indexes on a large batch, from classifier initialisations and from random
+    ones, also when the tables are coarsely quantised so that MANY scores tie exactly (exercises every tie rule)."""
+    K = 256
+    p = synth.synth_params(D, N, K, 11)
+    if quantised:
+        p = {k: (v * 4).round() / 4 for k, v in p.items()}
+    q = make_quantizer(D, N, K, p, DEV)
+    x = synth.synth_x(B, D, 4321)
+    if quantised:
+        x = (x * 2).round() / 2
+    xd = x.to(DEV)
+    P = _xct(q, xd)
+    _, gr = _prepared_views(q)
+    inits = [synth.synth_indexes(B, N, K, 5).numpy(),
+             q.encode(xd, refine_indexes_iters=0, as_bytes=False).cpu().numpy()]
+    for idx0 in inits:
+        outs = {}
+        for ver in ("v1", "v2"):
+            os.environ["MCQ_SEARCH"] = ver
+            try:
+                outs[ver] = _search(P, gr, idx0, N, K, 5)
+            finally:
+                del os.environ["MCQ_SEARCH"]
+        nbad = int((outs["v1"] != outs["v2"]).any(1).sum())
+        assert nbad == 0, f"{nbad}/{B} frames differ between the two search kernels"
+    # and both equal the bit-level CPU model on a prefix
+    n = 1024
+    NK = N * K
+    ref = gm.search(P[:n].cpu().numpy(), gr[:NK * NK].reshape(NK, NK).cpu().numpy(), inits[0][:n], N, K, 5)
+    assert np.array_equal(outs["v2"][:n], gm.search(P[:n].cpu().numpy(), gr[:NK * NK].reshape(NK, NK).cpu().numpy(),
+                                                    inits[1][:n], N, K, 5))
+    os.environ["MCQ_SEARCH"] = "v2"
+    try:
+        assert np.array_equal(_search(P[:n], gr, inits[0][:n], N, K, 5), ref)
+    finally:
+        del os.environ["MCQ_SEARCH"]
+
+
 @pytest.mark.parametrize("name", golden_case_names())
 def test_xct_accuracy(golden_cases, name):
     """P = x Cs^T from the tcgen05 bf16x3 GEMM (or the FFMA kernel for untiled shapes) against fp64."""
