@@ -13,6 +13,7 @@
  *                           (what compute_loss / QuantizerTrainer.step reach, :212, :652)
  *   mcq_decode           <- Quantizer.decode (:117-148) incl. _maybe_separate_indexes (:551-573)
  *   mcq_decode_backward  <- autograd of decode w.r.t. the scaled centers (used by compute_loss, :213-216)
+ *   mcq_class_loss_*     <- the log-softmax / chosen-logprob / mean-probability part of compute_loss (:218-240)
  *   mcq_encode_host      <- the same encode for a caller that holds HOST buffers (what a cgo/JNI/ctypes
  *                           host without its own CUDA plumbing binds)
  *
@@ -97,6 +98,24 @@ int mcq_decode_centers(const void *codes, int codes_dtype, int64_t num_frames, i
  * grad_scaled_centers (N,K,D) fp32 must be zeroed by the caller.  idx (B, N) int64. */
 int mcq_decode_backward(const float *grad_out, const int64_t *idx, int64_t num_frames, int num_codebooks,
                         int codebook_size, int dim, float *grad_scaled_centers, void *stream);
+
+/*
+ * Classifier-side losses of Quantizer.compute_loss (quantization.py:218-240) without its (B, N, K) intermediates.
+ * Forward: xw (Bp, N*K) fp32 receives fl(exp(logits_scale*speed) * x) . W^T (the bias-free part of
+ * Quantizer._logits, :277-279, from the tcgen05 GEMM; Bp = B rounded up to 128 rows, caller-allocated, kept for
+ * the backward pass);  *logprob_sum = sum_{b,n} log_softmax(xw + bias)[b, n, idx[b,n]]  (:221-225 before the mean);
+ * prob_sum (N*K) = sum_b softmax(xw + bias)[b, n, k]  (:235 before the mean).  idx (B, N) int64.
+ * Backward: grad_logits (B, N*K) = d loss / d logits given g_logprob_sum (1 element) and g_prob_sum (N*K), both
+ * DEVICE pointers (no host synchronisation).  The weight / bias / scale gradients are GEMMs of grad_logits the
+ * host layer forms (as the reference's autograd does).
+ */
+int mcq_class_loss_forward(const void *x, int x_dtype, int64_t num_frames, int dim, int num_codebooks,
+                           int codebook_size, const void *prepared, const int64_t *idx, float *xw,
+                           float *logprob_sum, float *prob_sum, void *workspace, size_t workspace_bytes,
+                           void *stream);
+int mcq_class_loss_backward(const float *xw, int64_t num_frames, int dim, int num_codebooks, int codebook_size,
+                            const void *prepared, const int64_t *idx, const float *g_logprob_sum,
+                            const float *g_prob_sum, float *grad_logits, void *stream);
 
 /* Pointers into the prepared blob (device): scaled centers (N*K, D) fp32 and the Gram table (N*K, N*K). */
 const float *mcq_prepared_scaled_centers(const void *prepared, int num_codebooks, int codebook_size, int dim);

@@ -393,6 +393,79 @@ int mcq_decode_backward(const float *grad_out, const int64_t *idx, int64_t B, in
     return launch_decode_backward(grad_out, idx, B, N, K, D, grad_scaled_centers, (cudaStream_t)stream);
 }
 
+int mcq_class_loss_forward(const void *x, int x_dtype, int64_t B, int D, int N, int K, const void *prepared,
+                           const int64_t *idx, float *xw, float *logprob_sum, float *prob_sum, void *workspace,
+                           size_t workspace_bytes, void *stream) {
+    int rc = check_shape(N, K, D);
+    if (rc) return rc;
+    if (B <= 0 || x_dtype < 0 || x_dtype > 2) {
+        set_error("mcq_class_loss_forward: bad argument (B=%lld)", (long long)B);
+        return MCQ_EINVAL;
+    }
+    if (!x || !prepared || !idx || !xw || !logprob_sum || !prob_sum || !workspace) {
+        set_error("mcq_class_loss_forward: null pointer");
+        return MCQ_EINVAL;
+    }
+    const Prepared L = prepared_layout(N, K, D);
+    const int64_t Bc = chunk_for(workspace_bytes, B, N, K, D);
+    if (Bc <= 0) {
+        set_error("mcq_class_loss_forward: workspace too small");
+        return MCQ_EINVAL;
+    }
+    const Workspace W = workspace_layout(Bc, N, K, D);
+    cudaStream_t st = (cudaStream_t)stream;
+    const char *blob = (const char *)prepared;
+    char *ws = (char *)workspace;
+    const bool tc = use_tensor_core_gemm() && L.NK % 64 == 0;
+    for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+        const int64_t nb = B - b0 < Bc ? B - b0 : Bc;
+        const char *xc = (const char *)x + (size_t)b0 * D * dtype_size(x_dtype);
+        float *out = xw + (size_t)b0 * L.NK;  // chunk starts are multiples of 128 rows: the GEMM writes in place
+        if ((rc = PROF(MCQ_PROF_OTHER, st, launch_split_x(xc, x_dtype, nb, L, blob, W, ws, true, st)))) return rc;
+        if (tc) {
+            const int64_t mp = (int64_t)align_up((size_t)nb, 128);
+            rc = PROF(MCQ_PROF_GEMM, st,
+                      launch_gemm_tc((const __nv_bfloat16 *)(ws + W.off_lsplit),
+                                     (const __nv_bfloat16 *)(blob + L.off_wsplit), out, mp, L.NK, L.Dp, st));
+        } else {
+            rc = PROF(MCQ_PROF_GEMM, st,
+                      launch_gemm_ffma((const float *)(ws + W.off_xf), (const float *)(blob + L.off_w), out, nb, L.NK,
+                                       L.D, (const float *)(blob + L.off_scal) + 1, st));
+        }
+        if (rc) return rc;
+    }
+    // partial sums live in the (now unused) P region of the workspace
+    const int ns = class_loss_streams(B, N);
+    float *part_prob = (float *)(ws + W.off_p);
+    const size_t need = sizeof(float) * ((size_t)ns * L.NK + (size_t)ns * N);
+    if (need > sizeof(float) * (size_t)W.Mp * L.NK) {
+        set_error("mcq_class_loss_forward: workspace too small for %d partial rows", ns);
+        return MCQ_EINVAL;
+    }
+    float *part_lp = part_prob + (size_t)ns * L.NK;
+    return PROF(MCQ_PROF_OTHER, st,
+                launch_class_loss_fwd(xw, (const float *)(blob + L.off_bias), idx, B, N, K, part_prob, part_lp, prob_sum,
+                                      logprob_sum, st));
+}
+
+int mcq_class_loss_backward(const float *xw, int64_t B, int D, int N, int K, const void *prepared, const int64_t *idx,
+                            const float *g_logprob_sum, const float *g_prob_sum, float *grad_logits, void *stream) {
+    int rc = check_shape(N, K, D);
+    if (rc) return rc;
+    if (B <= 0) {
+        set_error("mcq_class_loss_backward: bad argument");
+        return MCQ_EINVAL;
+    }
+    if (!xw || !prepared || !idx || !g_logprob_sum || !g_prob_sum || !grad_logits) {
+        set_error("mcq_class_loss_backward: null pointer");
+        return MCQ_EINVAL;
+    }
+    const Prepared L = prepared_layout(N, K, D);
+    return PROF(MCQ_PROF_OTHER, (cudaStream_t)stream,
+                launch_class_loss_bwd(xw, (const float *)((const char *)prepared + L.off_bias), idx, B, N, K,
+                                      g_logprob_sum, g_prob_sum, grad_logits, (cudaStream_t)stream));
+}
+
 int mcq_xct(const void *x, int x_dtype, int64_t B, int D, int N, int K, const void *prepared, float *P, void *workspace,
             size_t workspace_bytes, void *stream) {
     int rc = check_shape(N, K, D);

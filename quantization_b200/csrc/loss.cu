@@ -1,0 +1,256 @@
+// loss.cu -- the classifier-side losses of Quantizer.compute_loss (quantization.py:218-240) without the
+// (B, N, K) intermediates the reference materialises (log_softmax, exp, gather, one-hot counts, their autograd copies):
+//   forward : logprob_sum    = sum_{b,n} log_softmax(logits[b,n,:])[idx[b,n]]          (:221-225 before the mean)
+//             prob_sum[n,k]  = sum_b softmax(logits[b,n,:])[k]                          (:235 before the mean)
+//   backward: grad_logits[b,n,j] = g_lp * (1[j == idx] - s_j) + s_j * (c[n,j] - sum_k c[n,k] s_k),   s = softmax,
+//             g_lp = dL/dlogprob_sum, c = dL/dprob_sum.
+// logits = xw + bias where xw = fl(exp(logits_scale*speed) * x) . W^T comes from the tcgen05 GEMM (gemm_tc.cu).
+// Sums over frames are formed in a fixed order (per-warp partials over a strided frame set, then one pass over the
+// partials), so the losses are bit-reproducible from run to run -- no atomics.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mcq {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// reductions over aligned groups of W lanes (W = 16 or 32)
+template <int W>
+__device__ __forceinline__ float seg_max(float v) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+template <int W>
+__device__ __forceinline__ float seg_sum(float v) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v = v + __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// One row of K logits is handled by a segment of W lanes, EPL consecutive elements per lane (K = W * EPL, or
+// K < 16 = W with EPL = 1 and the upper lanes idle).  Returns softmax s[] and log-softmax ls[] of (xw + bias).
+template <int W, int EPL>
+__device__ __forceinline__ void row_softmax(const float *__restrict__ xw, const float *__restrict__ bias, int K,
+                                            int sl, float (&s)[EPL], float (&ls)[EPL]) {
+    float l[EPL];
+    if constexpr (EPL >= 4) {
+#pragma unroll
+        for (int t = 0; t < EPL; t += 4) {
+            const float4 a = *reinterpret_cast<const float4 *>(xw + sl * EPL + t);
+            const float4 c = __ldg(reinterpret_cast<const float4 *>(bias + sl * EPL + t));
+            l[t] = a.x + c.x;
+            l[t + 1] = a.y + c.y;
+            l[t + 2] = a.z + c.z;
+            l[t + 3] = a.w + c.w;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < EPL; ++t) {
+            const int k = sl * EPL + t;
+            l[t] = k < K ? xw[k] + __ldg(bias + k) : -INFINITY;
+        }
+    }
+    float m = l[0];
+#pragma unroll
+    for (int t = 1; t < EPL; ++t) m = fmaxf(m, l[t]);
+    m = seg_max<W>(m);
+    float sum = 0.0f;
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) {
+        s[t] = expf(l[t] - m);  // exp(-inf) = 0 for the idle lanes of K < 16
+        sum += s[t];
+    }
+    sum = seg_sum<W>(sum);
+    const float inv = 1.0f / sum, lsum = logf(sum);
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) {
+        s[t] = s[t] * inv;
+        ls[t] = (l[t] - m) - lsum;
+    }
+}
+
+// segment gs handles codebook n = gs % N and frames st, st + nstreams, ... with st = gs / N.
+template <int W, int EPL>
+__global__ void __launch_bounds__(256) class_loss_fwd_kernel(const float *__restrict__ xw, const float *__restrict__ bias,
+                                                             const int64_t *__restrict__ idx, int64_t B, int N, int K,
+                                                             int nstreams, float *__restrict__ part_prob,
+                                                             float *__restrict__ part_lp) {
+    constexpr int SPW = 32 / W;  // segments per warp
+    const int lane = threadIdx.x & 31, sl = lane % W;
+    const int gs = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * SPW + lane / W;
+    const bool live = gs < nstreams * N;  // dead segments still take part in the shuffles
+    const int n = live ? gs % N : 0, st = live ? gs / N : 0;
+    const size_t NK = (size_t)N * K;
+    float acc[EPL];
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) acc[t] = 0.0f;
+    float lp = 0.0f;
+    // all segments of a warp run the same number of iterations (shuffles are warp-wide)
+    for (int64_t b0 = 0; b0 < B; b0 += nstreams) {
+        const int64_t b = b0 + st;
+        const bool on = live && b < B;
+        const int64_t br = on ? b : 0;
+        float s[EPL], ls[EPL];
+        row_softmax<W, EPL>(xw + (size_t)br * NK + (size_t)n * K, bias + (size_t)n * K, K, sl, s, ls);
+        const int kc = (int)idx[(size_t)br * N + n];
+        if (on) {
+#pragma unroll
+            for (int t = 0; t < EPL; ++t) {
+                acc[t] += s[t];
+                if (sl * EPL + t == kc) lp += ls[t];
+            }
+        }
+    }
+    lp = seg_sum<W>(lp);
+    if (live) {
+#pragma unroll
+        for (int t = 0; t < EPL; ++t) {
+            const int k = sl * EPL + t;
+            if (k < K) part_prob[(size_t)st * NK + (size_t)n * K + k] = acc[t];
+        }
+        if (sl == 0) part_lp[(size_t)st * N + n] = lp;
+    }
+}
+
+// prob_sum[c] = sum over the partial rows, in a fixed order: 32 groups of threads sum every 32nd row, then the 32
+// group sums are added in group order.  Block = 32 columns x 32 groups.
+__global__ void __launch_bounds__(1024) class_loss_reduce_kernel(const float *__restrict__ part_prob,
+                                                                 const float *__restrict__ part_lp, int nstreams,
+                                                                 int N, int K, float *__restrict__ prob_sum,
+                                                                 float *__restrict__ logprob_sum) {
+    __shared__ float sm[32][33];
+    const int NK = N * K;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    float s = 0.0f;
+    if (c < NK) {
+#pragma unroll 4
+        for (int st = ty; st < nstreams; st += 32) s += part_prob[(size_t)st * NK + c];
+    }
+    sm[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < NK) {
+        float t = 0.0f;
+#pragma unroll
+        for (int g = 0; g < 32; ++g) t += sm[g][tx];
+        prob_sum[c] = t;
+    }
+    if (blockIdx.x == 0 && ty == 1) {  // the scalar: fixed-order per-lane partials, then a shuffle tree
+        float t = 0.0f;
+        for (int i = tx; i < nstreams * N; i += 32) t += part_lp[i];
+        t = seg_sum<32>(t);
+        if (tx == 0) *logprob_sum = t;
+    }
+}
+
+template <int W, int EPL>
+__global__ void __launch_bounds__(256) class_loss_bwd_kernel(const float *__restrict__ xw, const float *__restrict__ bias,
+                                                             const int64_t *__restrict__ idx, int64_t B, int N, int K,
+                                                             const float *__restrict__ g_lp,
+                                                             const float *__restrict__ g_prob,
+                                                             float *__restrict__ grad_logits) {
+    constexpr int SPW = 32 / W;
+    const int lane = threadIdx.x & 31, sl = lane % W;
+    const int64_t rows = B * N;
+    const size_t NK = (size_t)N * K;
+    const float glp = *g_lp;
+    const int64_t nseg = (int64_t)gridDim.x * (blockDim.x >> 5) * SPW;
+    for (int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * SPW; r0 < rows; r0 += nseg) {
+        const int64_t r = r0 + lane / W;
+        const bool on = r < rows;
+        const int64_t rr = on ? r : 0;
+        const int64_t b = rr / N;
+        const int n = (int)(rr - b * N);
+        float s[EPL], ls[EPL];
+        row_softmax<W, EPL>(xw + (size_t)b * NK + (size_t)n * K, bias + (size_t)n * K, K, sl, s, ls);
+        const int kc = (int)idx[rr];
+        float c[EPL];
+        float dotc = 0.0f;
+#pragma unroll
+        for (int t = 0; t < EPL; ++t) {
+            const int k = sl * EPL + t;
+            c[t] = k < K ? __ldg(g_prob + (size_t)n * K + k) : 0.0f;
+            dotc += c[t] * s[t];
+        }
+        dotc = seg_sum<W>(dotc);
+        float *g = grad_logits + (size_t)b * NK + (size_t)n * K + sl * EPL;
+        float o[EPL];
+#pragma unroll
+        for (int t = 0; t < EPL; ++t) o[t] = glp * ((sl * EPL + t == kc ? 1.0f : 0.0f) - s[t]) + s[t] * (c[t] - dotc);
+        if (on) {
+            if constexpr (EPL >= 4) {
+#pragma unroll
+                for (int t = 0; t < EPL; t += 4)
+                    *reinterpret_cast<float4 *>(g + t) = make_float4(o[t], o[t + 1], o[t + 2], o[t + 3]);
+            } else {
+#pragma unroll
+                for (int t = 0; t < EPL; ++t)
+                    if (sl * EPL + t < K) g[t] = o[t];
+            }
+        }
+    }
+}
+
+// K -> (segment width, elements per lane)
+#define MCQ_LOSS_DISPATCH(K, CALL)                 \
+    switch (K) {                                   \
+        case 256: CALL(32, 8); break;              \
+        case 128: CALL(32, 4); break;              \
+        case 64: CALL(32, 2); break;               \
+        case 32: CALL(32, 1); break;               \
+        default: CALL(16, 1); break; /* K <= 16 */ \
+    }
+
+}  // namespace
+
+// number of frame streams (and so of partial rows) the forward kernel uses for a batch of B frames
+int class_loss_streams(int64_t B, int N) {
+    int64_t segs = (int64_t)148 * 4 * 8;  // 4 CTAs of 8 warps per SM
+    int64_t st = segs / N;
+    if (st > B / 2) st = B / 2;  // the partial rows live in a region of (B rounded up to 128) x N*K floats
+    if (st < 1) st = 1;
+    return (int)st;
+}
+
+int launch_class_loss_fwd(const float *xw, const float *bias, const int64_t *idx, int64_t B, int N, int K,
+                          float *part_prob, float *part_lp, float *prob_sum, float *logprob_sum, cudaStream_t st) {
+    if (K > 256) {
+        set_error("class loss: codebook_size %d > 256", K);
+        return MCQ_EUNSUPPORTED;
+    }
+    const int ns = class_loss_streams(B, N);
+    const int spw = K >= 32 ? 1 : 2;
+    const int warps = (ns * N + spw - 1) / spw;
+    const int blocks = (warps + 7) / 8;
+#define MCQ_FWD(W, EPL) \
+    class_loss_fwd_kernel<W, EPL><<<blocks, 256, 0, st>>>(xw, bias, idx, B, N, K, ns, part_prob, part_lp)
+    MCQ_LOSS_DISPATCH(K, MCQ_FWD)
+#undef MCQ_FWD
+    MCQ_LAUNCH_CHECK("class_loss_fwd_kernel");
+    class_loss_reduce_kernel<<<(N * K + 31) / 32, 1024, 0, st>>>(part_prob, part_lp, ns, N, K, prob_sum, logprob_sum);
+    MCQ_LAUNCH_CHECK("class_loss_reduce_kernel");
+    return MCQ_OK;
+}
+
+int launch_class_loss_bwd(const float *xw, const float *bias, const int64_t *idx, int64_t B, int N, int K,
+                          const float *g_lp, const float *g_prob, float *grad_logits, cudaStream_t st) {
+    if (K > 256) {
+        set_error("class loss: codebook_size %d > 256", K);
+        return MCQ_EUNSUPPORTED;
+    }
+    const int spw = K >= 32 ? 1 : 2;
+    int64_t blocks = (B * N + 8 * spw - 1) / (8 * spw);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+#define MCQ_BWD(W, EPL) \
+    class_loss_bwd_kernel<W, EPL><<<(unsigned)blocks, 256, 0, st>>>(xw, bias, idx, B, N, K, g_lp, g_prob, grad_logits)
+    MCQ_LOSS_DISPATCH(K, MCQ_BWD)
+#undef MCQ_BWD
+    MCQ_LAUNCH_CHECK("class_loss_bwd_kernel");
+    return MCQ_OK;
+}
+
+}  // namespace mcq

@@ -378,25 +378,34 @@ def test_encode_host_matches_device():
     assert torch.equal(q.encode_host(x), out)  # pageable host memory works too
 
 
-def test_compute_loss_and_gradients():
-    """compute_loss values and gradients against a plain-PyTorch evaluation on the same indexes."""
-    p = synth.synth_params(64, 4, 16, 2)
-    q = make_quantizer(64, 4, 16, p, DEV, centers_scale=0.01, logits_scale=-0.01)
-    x = synth.synth_x(512, 64, 5).to(DEV)
+@pytest.mark.parametrize("K,N,B", [(16, 4, 512), (256, 4, 1000), (64, 2, 777), (32, 8, 130)])
+def test_compute_loss_and_gradients(K, N, B):
+    """compute_loss values and gradients against a plain-PyTorch evaluation on the same indexes (K >= 32 goes
+    through the fused classifier-loss kernels, mcq_class_loss_forward / _backward; K = 16 through PyTorch)."""
+    p = synth.synth_params(64, N, K, 2)
+    q = make_quantizer(64, N, K, p, DEV, centers_scale=0.01, logits_scale=-0.01)
+    x = synth.synth_x(B, 64, 5).to(DEV)
     losses = q.compute_loss(x, 2)
     (losses[0] + losses[1] + 0.01 * losses[2]).backward()
     g_ours = {n: v.grad.clone() for n, v in q.named_parameters()}
     q.zero_grad()
     idx = q._compute_indexes(x, 2)
     cs = q.get_centers()
-    xa = sum(cs[n][idx[:, n]] for n in range(4))
+    xa = sum(cs[n][idx[:, n]] for n in range(N))
     rel = ((xa - x) ** 2).sum() / (((x - q.get_data_mean()) ** 2).sum() + 1e-20)
-    lg = q._logits(x).reshape(-1, 4, 16).log_softmax(2)
+    lg = q._logits(x).reshape(-1, N, K).log_softmax(2)
     lp = -torch.gather(lg, 2, idx.unsqueeze(2)).mean()
     probs = lg.exp().mean(0) + 1e-20
-    le = (np.log(16) - (-(probs * probs.log()).sum(1).mean())) / np.log(16)
+    le = (np.log(K) - (-(probs * probs.log()).sum(1).mean())) / np.log(K)
     (rel + lp + 0.01 * le).backward()
     assert torch.allclose(losses[0], rel, rtol=1e-5) and torch.allclose(losses[1], lp, rtol=1e-5)
+    assert torch.allclose(losses[2], le, rtol=1e-4, atol=1e-7)
+    cnt = torch.zeros(N, K, device=DEV)
+    for n in range(N):
+        cnt[n] = torch.bincount(idx[:, n], minlength=K).float()
+    ac = cnt / B + 1e-20
+    ie = (np.log(K) - (-(ac * ac.log()).sum(1).mean())) / np.log(K)
+    assert torch.allclose(losses[3], ie, rtol=1e-5, atol=1e-7)
     for n, v in q.named_parameters():
         assert torch.allclose(g_ours[n], v.grad, rtol=1e-4, atol=1e-7), n
 

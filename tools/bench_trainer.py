@@ -53,3 +53,39 @@ tr.cur_iter = tr.phase_one_iters
 tr.step(x)  # switches to phase 2 (get_product_quantizer)
 tr.cur_iter = tr.phase_one_iters + 2
 run(tr, "phase 2")
+
+
+# ---- the unmodified reference trainer (baseline/_ref) on the same GPU, same batch (upcast: the reference
+# raises on bf16 frames with fp32 parameters, quantization.py:277-279; its own usage upcasts, test_train_hdf5.py:30)
+ref_dir = os.path.join(ROOT, "baseline", "_ref")
+if os.path.isdir(os.path.join(ref_dir, "quantization")):
+    import types
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+    sys.path.insert(0, ref_dir)
+    import quantization as refq
+    xf = x.float()
+
+    def run_ref(tr, tag, n):
+        for _ in range(2):
+            tr.step(xf)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            tr.step(xf)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        q = tr.quantizer
+        print(f"reference {tag}: K={q.codebook_size} N={q.num_codebooks} B={B}: {ms:.2f} ms/step; "
+              f"20,001 steps = {ms * 20001 / 1e3:.0f} s", flush=True)
+
+    torch.manual_seed(1)
+    random.seed(1)
+    rt = refq.QuantizerTrainer(dim=D, bytes_per_frame=4, device=dev, phase_one_iters=10000, phase_two_iters=10000)
+    rt.cur_iter = 1
+    run_ref(rt, "phase 1", 5)
+    rt.cur_iter = rt.phase_one_iters
+    rt.step(xf)
+    rt.cur_iter = rt.phase_one_iters + 2
+    run_ref(rt, "phase 2", 5)
