@@ -110,6 +110,15 @@ class ClockSampler:
         return out
 
 
+def host_threads():
+    """Threads the CPU arm uses: every core this process may run on.  (torchrun exports OMP_NUM_THREADS=1, which would
+    silently make the 'all host threads' baseline single-threaded, so the count is passed explicitly.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_port_run(x_np, params, threads=0):
     """One pass of the CPU port (oracle) over x_np.  Returns (seconds, indexes)."""
     import oracle
@@ -172,10 +181,10 @@ def run_reference(args, rank, world):
     from quantization_b200 import synth
     params = synth.synth_params(DIM, NCB, KSZ, 0)
     x = synth.synth_x(CPU_SAMPLE, DIM, 1234 + 1).numpy()
-    cores = oracle.max_threads()
+    cores = host_threads()
     for _ in range(args.warmup):
-        cpu_port_run(x, params)
-    times = [cpu_port_run(x, params)[0] for _ in range(args.steps)]
+        cpu_port_run(x, params, cores)
+    times = [cpu_port_run(x, params, cores)[0] for _ in range(args.steps)]
     sec = sum(times) / len(times)
     value = CPU_SAMPLE / sec / 1e6
     line = {
@@ -341,9 +350,9 @@ def run_ours(args, rank, world, local_rank):
         import numpy as np
         xs = x_host[:CPU_SAMPLE].numpy()
         import oracle
-        cores = oracle.max_threads()
-        cpu_port_run(xs[:512], params)
-        sec, ref_idx = cpu_port_run(xs, params)
+        cores = host_threads()
+        cpu_port_run(xs[:512], params, cores)
+        sec, ref_idx = cpu_port_run(xs, params, cores)
         ours = codes[:CPU_SAMPLE].cpu().numpy().astype(np.int64)
         c64 = params["centers"].numpy().astype(np.float64)
         x64 = xs.astype(np.float64)
