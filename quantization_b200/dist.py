@@ -49,3 +49,28 @@ def sharded_encode(quantizer, x_local: torch.Tensor, num_frames_total: int, refi
     x2 = x_local.reshape(-1, x_local.shape[-1])
     codes_local = encode_fn(x2)
     return all_gather_codes(codes_local, num_frames_total, group=group)
+
+
+def sharded_round_trip_error(quantizer, x_local: torch.Tensor, refine_indexes_iters: int = 5, group=None,
+                             encode_fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
+                             decode_fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None):
+    """encode -> decode round trip of every rank's row block and the job-wide relative reconstruction error
+    sum((x - x_hat)^2) / sum(x^2) (BASELINE config 5: the MSE sweep over 1/2/4/8 GPUs).  The only exchange is one
+    all-reduce of two float64 scalars; frames and codes stay on their rank.  Returns (rel_error, codes_local).
+    `encode_fn` / `decode_fn` default to the quantizer's CUDA path; the CPU tests inject stand-ins."""
+    if encode_fn is None:
+        def encode_fn(t):
+            return quantizer.encode(t, refine_indexes_iters=refine_indexes_iters, as_bytes=True)
+    if decode_fn is None:
+        def decode_fn(c):
+            with torch.no_grad():
+                return quantizer.decode(c)
+    x2 = x_local.reshape(-1, x_local.shape[-1])
+    codes = encode_fn(x2)
+    xf = x2.to(torch.float32)
+    err = decode_fn(codes).to(torch.float32) - xf
+    # float64 partial sums: the result does not depend on how the frames are split over the ranks beyond 1e-12
+    sums = torch.stack([(err.double() ** 2).sum(), (xf.double() ** 2).sum()])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    return float(sums[0] / sums[1]), codes
