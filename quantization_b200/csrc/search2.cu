@@ -91,8 +91,8 @@ struct alignas(16) WarpMem2 {
 
 // The R smallest of the warp's 256 candidates (8 per lane; candidate t of a lane has flat index flat[t], ascending in
 // t), ascending by (key, flat), written to s.sel[0..R).  quantization.py:474-487 (sort + keep the first K_cutoff).
-template <int N, int R>
-__device__ __forceinline__ void select_sorted(WarpMem2<N> &s, const float (&key)[8], const int (&flat)[8], int lane) {
+template <class Mem, int R>
+__device__ __forceinline__ void select_sorted(Mem &s, const float (&key)[8], const int (&flat)[8], int lane) {
     // rank of key[t] among the lane's 8 keys, equal keys in index order:
     //   rank[t] = #{u < t: key[u] <= key[t]} + #{u > t: key[u] < key[t]}
     int rank[8];
@@ -145,9 +145,8 @@ __device__ __forceinline__ int select_best(const float (&key)[8], const int (&fl
 
 // Level 1 (quantization.py:401-418 with the per-codebook constants dropped) + top-16 per codebook.
 // Lane L owns entries 4L..4L+3 and 128+4L..128+4L+3, so every float4 request of the warp is 512 contiguous bytes.
-template <int N>
-__device__ __forceinline__ void level1(WarpMem2<N> &s, const float *__restrict__ Pb, const float *__restrict__ Gp,
-                                       int lane) {
+template <int N, class Mem>
+__device__ __forceinline__ void level1(Mem &s, const float *__restrict__ Pb, const float *__restrict__ Gp, int lane) {
     constexpr unsigned NK = N * K2;
     const float *diag = Gp + (size_t)NK * NK;
     int flat[8];
@@ -159,7 +158,7 @@ __device__ __forceinline__ void level1(WarpMem2<N> &s, const float *__restrict__
 #pragma unroll
         for (int t = 0; t < 8; ++t) acc[t] = 0.0f;
         const unsigned colbase = n * K2 + lane * 4;
-#pragma unroll
+#pragma unroll(N <= 8 ? N - 1 : 5)  // rows in flight per batch: all N-1 up to 8 codebooks, 5 of the 15 at N = 16
         for (int mm = 0; mm < N - 1; ++mm) {
             const int m = mm + (mm >= n ? 1 : 0);  // ascending m, skipping n
             const float4 *row = reinterpret_cast<const float4 *>(Gp + (s.rowoff[m] + colbase));
@@ -191,7 +190,7 @@ __device__ __forceinline__ void level1(WarpMem2<N> &s, const float *__restrict__
         float key[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) key[t] = v[t] - vold;
-        select_sorted<N, 16>(s, key, flat, lane);
+        select_sorted<Mem, 16>(s, key, flat, lane);
         if (lane < 16) {
             const float2 r = s.sel[lane];
             s.kd1[n][lane] = r.x;
@@ -270,7 +269,7 @@ __device__ __forceinline__ void merge1(WarpMem2<N> &s, const GSrc &G, int g, int
         }
         __syncwarp();
     } else {
-        select_sorted<N, 16>(s, key, flat, lane);
+        select_sorted<WarpMem2<N>, 16>(s, key, flat, lane);
         if (lane < 16) {
             const float2 r = s.sel[lane];
             const int fl = __float_as_int(r.y);
@@ -343,7 +342,7 @@ __device__ __forceinline__ void merge2(WarpMem2<N> &s, const GSrc &G, int g, int
         }
         __syncwarp();
     } else {
-        select_sorted<N, 32>(s, key, flat, lane);
+        select_sorted<WarpMem2<N>, 32>(s, key, flat, lane);
         {
             const float2 r = s.sel[lane];
             const int fl = __float_as_int(r.y);
@@ -453,7 +452,7 @@ template <int N, bool TEX>
 __device__ __forceinline__ void refine_pass2(WarpMem2<N> &s, const float *__restrict__ Pb, const GSrc &G, int lane) {
     if (lane < N) s.rowoff[lane] = (unsigned)(lane * K2 + s.old[lane]) * (unsigned)(N * K2);
     __syncwarp();
-    level1<N>(s, Pb, G.g, lane);
+    level1<N, WarpMem2<N>>(s, Pb, G.g, lane);
     gather_uv<N, TEX>(s, G, lane);
     if constexpr (N == 2) {
         merge1<N, TEX, true>(s, G, 0, lane);
@@ -469,6 +468,367 @@ __device__ __forceinline__ void refine_pass2(WarpMem2<N> &s, const float *__rest
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 16 codebooks (BASELINE config 4).  Same building blocks; the differences to the N <= 8 path:
+//   * the u/v terms do not fit shared memory for all 240 codebook pairs (16 KB), so each merge gathers the ones of ITS
+//     pairs into a 2 KB buffer first (ul / vl);
+//   * one more level: the quad merges (32 x 32) keep 32 of 1024 candidates (four 256-candidate selections + one over
+//     their 128 survivors), and the final merge joins two octets: 64 tables, eight per right-hand codebook.
+struct alignas(16) WarpMem16 {
+    union {
+        float2 lists[9][32];
+        float es[32][TSTR];
+    };
+    union {
+        float tab[TAB_FLOATS];  // T_ab of the wide merges
+        float2 cand[4][32];     // survivors of the four 256-candidate selections of a quad merge
+    };
+    float kd1[16][16];
+    int kk[16][16];
+    unsigned rowk[16][16];
+    float ul[16][16];        // u terms of the current merge: ul[c][p] = G[(b,old_b), (a, kk_a[p])], c = pair index
+    float vl[16][16];        // v terms: vl[c][q] = G[(a,old_a), (b, kk_b[q])]
+    float2 sel[32];
+    float kd2[8][16];
+    unsigned kt2[8][16];     // 2 slots (8 bits)
+    float kd3[4][32];
+    unsigned kt3[4][32];     // 4 slots (16 bits)
+    float kd4[2][32];
+    unsigned kt4[2][32];     // 8 slots (32 bits)
+    int old[16];
+    unsigned rowoff[16];
+    unsigned used[16];
+};
+
+// ul/vl of the NA x NB codebook pairs (a_base + la, b_base + lb), pair index c = la * NB + lb.
+// Lanes 0..15 fetch u (slot p = lane), lanes 16..31 fetch v (slot q = lane - 16).
+template <int NA, int NB>
+__device__ __forceinline__ void gather_uv_local(WarpMem16 &s, const GSrc &G, int a_base, int b_base, int lane) {
+    const int sl = lane & 15;
+    const bool isv = lane >= 16;
+    constexpr int NC = NA * NB;
+    constexpr int BATCH = NC < 4 ? NC : 4;
+#pragma unroll 1
+    for (int c0 = 0; c0 < NC; c0 += BATCH) {
+        float val[BATCH];
+#pragma unroll
+        for (int cc = 0; cc < BATCH; ++cc) {
+            const int c = c0 + cc;
+            const int a = a_base + c / NB, b = b_base + c % NB;
+            // u: row of (b, old_b), column (a, kk_a[p]);  v: row of (a, old_a), column (b, kk_b[q])
+            const unsigned idx = isv ? s.rowoff[a] + b * K2 + s.kk[b][sl] : s.rowoff[b] + a * K2 + s.kk[a][sl];
+            val[cc] = gat<false>(G, idx);
+        }
+#pragma unroll
+        for (int cc = 0; cc < BATCH; ++cc) {
+            if (isv)
+                s.vl[c0 + cc][sl] = val[cc];
+            else
+                s.ul[c0 + cc][sl] = val[cc];
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void merge1_16(WarpMem16 &s, const GSrc &G, int g, int lane) {
+    const int e = 2 * g, o = e + 1;
+    gather_uv_local<1, 1>(s, G, e, o, lane);
+    const int j = lane & 15, ib = (lane >> 4) * 8;
+    const unsigned ko = o * K2 + s.kk[o][j];
+    const float v = s.vl[0][j];
+    const float kdo = s.kd1[o][j];
+    const float w = gat<false>(G, s.rowoff[e] + o * K2 + s.old[o]);
+    float key[8];
+    int flat[8];
+    float gv[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) gv[t] = gat<false>(G, s.rowk[e][ib + t] + ko);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const float d = ((gv[t] - s.ul[0][ib + t]) - v) + w;
+        key[t] = fmaf(2.0f, d, s.kd1[e][ib + t] + kdo);
+        flat[t] = (ib + t) * 16 + j;
+    }
+    select_sorted<WarpMem16, 16>(s, key, flat, lane);
+    if (lane < 16) {
+        const float2 r = s.sel[lane];
+        const int fl = __float_as_int(r.y);
+        s.kd2[g][lane] = r.x;
+        s.kt2[g][lane] = (unsigned)(fl >> 4) | ((unsigned)(fl & 15) << 4);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void merge2_16(WarpMem16 &s, const GSrc &G, int g, int lane) {
+    const int e = 2 * g, o = e + 1;
+    const int a0 = 4 * g, a1 = a0 + 1, b0 = a0 + 2, b1 = a0 + 3;
+    gather_uv_local<2, 2>(s, G, a0, b0, lane);  // pair index c = la * 2 + lb
+    const int j = lane & 15, ib = (lane >> 4) * 8;
+    const unsigned tj = s.kt2[o][j];
+    const int q0 = tj & 15, q1 = tj >> 4;
+    const unsigned c0 = b0 * K2 + s.kk[b0][q0], c1 = b1 * K2 + s.kk[b1][q1];
+    const float v00 = s.vl[0][q0], v10 = s.vl[2][q0], v01 = s.vl[1][q1], v11 = s.vl[3][q1];
+    const float kdo = s.kd2[o][j];
+    const unsigned cb0 = b0 * K2 + s.old[b0], cb1 = b1 * K2 + s.old[b1];
+    const float w00 = gat<false>(G, s.rowoff[a0] + cb0), w10 = gat<false>(G, s.rowoff[a1] + cb0);
+    const float w01 = gat<false>(G, s.rowoff[a0] + cb1), w11 = gat<false>(G, s.rowoff[a1] + cb1);
+    float g00[8], g10[8], g01[8], g11[8];
+    unsigned tis[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        tis[t] = s.kt2[e][ib + t];
+        const unsigned rp0 = s.rowk[a0][tis[t] & 15], rp1 = s.rowk[a1][tis[t] >> 4];
+        g00[t] = gat<false>(G, rp0 + c0);
+        g10[t] = gat<false>(G, rp1 + c0);
+        g01[t] = gat<false>(G, rp0 + c1);
+        g11[t] = gat<false>(G, rp1 + c1);
+    }
+    float key[8];
+    int flat[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int ia0 = tis[t] & 15, ia1 = tis[t] >> 4;
+        const float d00 = ((g00[t] - s.ul[0][ia0]) - v00) + w00;
+        const float d10 = ((g10[t] - s.ul[2][ia1]) - v10) + w10;
+        const float d01 = ((g01[t] - s.ul[1][ia0]) - v01) + w01;
+        const float d11 = ((g11[t] - s.ul[3][ia1]) - v11) + w11;
+        const float wb0 = d00 + d10, wb1 = d01 + d11;
+        const float dot = wb0 + wb1;
+        key[t] = fmaf(2.0f, dot, s.kd2[e][ib + t] + kdo);
+        flat[t] = (ib + t) * 16 + j;
+    }
+    select_sorted<WarpMem16, 32>(s, key, flat, lane);
+    {
+        const float2 r = s.sel[lane];
+        const int fl = __float_as_int(r.y);
+        s.kd3[g][lane] = r.x;
+        s.kt3[g][lane] = s.kt2[e][fl >> 4] | (s.kt2[o][fl & 15] << 8);
+    }
+    __syncwarp();
+}
+
+// dot(i, j) of the 32 x 32 joint candidates of two groups of NA codebooks each (a_base.., b_base..), lane = column j,
+// dot[i] over the rows i.  ti / tj: this lane's slot tuple as row i = lane / as column j = lane (4 bits per codebook).
+template <int NA>
+__device__ __forceinline__ void wide_dots(WarpMem16 &s, const GSrc &G, int a_base, int b_base, unsigned ti, unsigned tj,
+                                          int lane, float (&dot)[32]) {
+#pragma unroll
+    for (int c = 0; c < NA; ++c) {
+        const unsigned ua = __reduce_or_sync(FULL, 1u << ((ti >> (4 * c)) & 15));
+        const unsigned ub = __reduce_or_sync(FULL, 1u << ((tj >> (4 * c)) & 15));
+        if (lane == 0) {
+            s.used[c] = ua;
+            s.used[8 + c] = ub;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dot[i] = 0.0f;
+    if constexpr (NA == 4) gather_uv_local<4, 4>(s, G, a_base, b_base, lane);  // all 16 pairs fit: c = la * 4 + lb
+    const int q = lane & 15, pb = (lane >> 4) * 8;
+#pragma unroll 1
+    for (int lb = 0; lb < NA; ++lb) {
+        const int b = b_base + lb;
+        if constexpr (NA == 8) gather_uv_local<8, 1>(s, G, a_base, b, lane);   // the 8 pairs of this b: c = la
+        const unsigned cq = b * K2 + s.kk[b][q];
+        const bool colu = (s.used[8 + lb] >> q) & 1u;
+        const unsigned cbo = b * K2 + s.old[b];
+        float E[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) E[c] = 0.0f;
+#pragma unroll 1
+        for (int la = 0; la < NA; ++la) {
+            const int a = a_base + la;
+            const int c = (NA == 4) ? la * 4 + lb : la;
+            const unsigned msk = colu ? (s.used[la] >> pb) & 0xffu : 0u;
+            unsigned ra[8];
+            float u[8];
+            {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(&s.rowk[a][pb]);
+                const float4 *up = reinterpret_cast<const float4 *>(&s.ul[c][pb]);
+                const uint4 r0 = rp[0], r1 = rp[1];
+                const float4 u0 = up[0], u1 = up[1];
+                ra[0] = r0.x; ra[1] = r0.y; ra[2] = r0.z; ra[3] = r0.w; ra[4] = r1.x; ra[5] = r1.y; ra[6] = r1.z; ra[7] = r1.w;
+                u[0] = u0.x; u[1] = u0.y; u[2] = u0.z; u[3] = u0.w; u[4] = u1.x; u[5] = u1.y; u[6] = u1.z; u[7] = u1.w;
+            }
+            float gv[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                gv[t] = 0.0f;
+                if ((msk >> t) & 1u) gv[t] = gat<false>(G, ra[t] + cq);
+            }
+            const float v = s.vl[c][q];
+            const float w = gat<false>(G, s.rowoff[a] + cbo);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) s.tab[trow_off(pb + t) + q] = ((gv[t] - u[t]) - v) + w;
+            __syncwarp();
+            const float4 *mine = reinterpret_cast<const float4 *>(&s.tab[trow_off((ti >> (4 * la)) & 15)]);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const float4 r = mine[cc];
+                fadd2(E[4 * cc + 0], E[4 * cc + 1], r.x, r.y);
+                fadd2(E[4 * cc + 2], E[4 * cc + 3], r.z, r.w);
+            }
+            __syncwarp();
+        }
+        float4 *erow = reinterpret_cast<float4 *>(&s.es[lane][0]);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) erow[cc] = make_float4(E[4 * cc], E[4 * cc + 1], E[4 * cc + 2], E[4 * cc + 3]);
+        __syncwarp();
+        const int jq = (tj >> (4 * lb)) & 15;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dot[i] = dot[i] + s.es[i][jq];
+        __syncwarp();
+    }
+    s.lists[8][lane] = make_float2(__int_as_float(0x7f800000), __int_as_float(0));  // es overwrote the sentinels
+    __syncwarp();
+}
+
+// Quad merge of N = 16 (not final): groups e = 2g (codebooks 8g..8g+3) and o = 2g+1 (8g+4..8g+7); keeps the 32 best
+// of the 1024 joint candidates, ascending by (score, flat = i*32 + j).
+__device__ __forceinline__ void merge4_16(WarpMem16 &s, const GSrc &G, int g, int lane) {
+    const int e = 2 * g, o = e + 1;
+    const unsigned ti = s.kt3[e][lane], tj = s.kt3[o][lane];
+    float dot[32];
+    wide_dots<4>(s, G, 8 * g, 8 * g + 4, ti, tj, lane, dot);
+    const float kdo = s.kd3[o][lane];
+    // four selections over the row blocks i in [8r, 8r+8), then one over their 4 x 32 survivors
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float key[8];
+        int flat[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            key[t] = fmaf(2.0f, dot[8 * r + t], s.kd3[e][8 * r + t] + kdo);
+            flat[t] = (8 * r + t) * 32 + lane;
+        }
+        select_sorted<WarpMem16, 32>(s, key, flat, lane);
+        s.cand[r][lane] = s.sel[lane];
+        __syncwarp();
+    }
+    {
+        float key[8];
+        int flat[8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 c = s.cand[t][lane];  // block t holds flats in [256 t, 256 t + 256): ascending in t
+            key[t] = c.x;
+            flat[t] = __float_as_int(c.y);
+        }
+#pragma unroll
+        for (int t = 4; t < 8; ++t) {
+            key[t] = __int_as_float(0x7f800000);
+            flat[t] = 0x7ffffff0 + t;
+        }
+        select_sorted<WarpMem16, 32>(s, key, flat, lane);
+    }
+    {
+        const float2 r = s.sel[lane];
+        const int fl = __float_as_int(r.y) & 1023;
+        s.kd4[g][lane] = r.x;
+        s.kt4[g][lane] = s.kt3[e][fl >> 5] | (s.kt3[o][fl & 31] << 16);
+    }
+    __syncwarp();
+}
+
+// Final merge of N = 16: the two octets, 32 x 32 candidates, best one wins.
+__device__ __forceinline__ void merge8_final_16(WarpMem16 &s, const GSrc &G, int lane) {
+    const unsigned ti = s.kt4[0][lane], tj = s.kt4[1][lane];
+    float dot[32];
+    wide_dots<8>(s, G, 0, 8, ti, tj, lane, dot);
+    const float kdo = s.kd4[1][lane];
+    float best = fmaf(2.0f, dot[0], s.kd4[0][0] + kdo);
+    int bi = 0;
+#pragma unroll
+    for (int i = 1; i < 32; ++i) {
+        const float key = fmaf(2.0f, dot[i], s.kd4[0][i] + kdo);
+        if (key < best) {
+            best = key;
+            bi = i;
+        }
+    }
+    const float m = credux_min(best);
+    const unsigned c = (best == m) ? (unsigned)(bi * 32 + lane) : 0x7fffffffu;
+    unsigned flat = __reduce_min_sync(FULL, c);
+    if (flat == 0x7fffffffu) flat = 0;  // only reachable with NaN scores
+    const unsigned te = s.kt4[0][flat >> 5], to = s.kt4[1][flat & 31];
+    if (lane < 16) {
+        const unsigned tt = lane < 8 ? te : to;
+        s.old[lane] = s.kk[lane][(tt >> (4 * (lane & 7))) & 15];
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void refine_pass16(WarpMem16 &s, const float *__restrict__ Pb, const GSrc &G, int lane) {
+    if (lane < 16) s.rowoff[lane] = (unsigned)(lane * K2 + s.old[lane]) * (unsigned)(16 * K2);
+    __syncwarp();
+    level1<16, WarpMem16>(s, Pb, G.g, lane);
+#pragma unroll 1
+    for (int g = 0; g < 8; ++g) merge1_16(s, G, g, lane);
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) merge2_16(s, G, g, lane);
+#pragma unroll 1
+    for (int g = 0; g < 2; ++g) merge4_16(s, G, g, lane);
+    merge8_final_16(s, G, lane);
+}
+
+constexpr int WPC16 = 4;
+
+__global__ void __launch_bounds__(WPC16 * 32, 4)
+    search2_kernel16(const float *__restrict__ P, GSrc G, int64_t B, int iters, const int32_t *__restrict__ idx_in,
+                     int32_t *__restrict__ idx_out, unsigned *__restrict__ work_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpMem16 &s = reinterpret_cast<WarpMem16 *>(smem_raw)[warp];
+    s.lists[8][lane] = make_float2(__int_as_float(0x7f800000), __int_as_float(0));
+    s.sel[lane] = make_float2(0.0f, __int_as_float(0));
+    __syncwarp();
+    const int64_t nwarps = (int64_t)gridDim.x * WPC16;
+    for (int64_t b = (int64_t)blockIdx.x * WPC16 + warp; b < B;) {
+        if (lane < 16) s.old[lane] = idx_in[(size_t)b * 16 + lane];
+        __syncwarp();
+        const float *Pb = P + (size_t)b * (16 * K2);
+#pragma unroll 1
+        for (int it = 0; it < iters; ++it) {
+            const int prev = (lane < 16) ? s.old[lane] : 0;
+            refine_pass16(s, Pb, G, lane);
+            const int now = (lane < 16) ? s.old[lane] : 0;
+            if (__all_sync(FULL, prev == now)) break;  // fixed point: the remaining passes are no-ops
+        }
+        if (lane < 16) idx_out[(size_t)b * 16 + lane] = s.old[lane];
+        if (work_counter != nullptr) {
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(work_counter, 1u);
+            b = nwarps + (int64_t)__shfl_sync(FULL, t, 0);
+        } else {
+            b += nwarps;
+        }
+        __syncwarp();
+    }
+}
+
+int launch16(const float *P, const float *Gp, int64_t B, int iters, const int32_t *idx_in, int32_t *idx_out,
+             cudaStream_t st, unsigned *work_counter) {
+    GSrc G{Gp};
+    const size_t smem = sizeof(WarpMem16) * WPC16;
+    auto kern = search2_kernel16;
+    MCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    MCQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WPC16 * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    int dev = 0, sms = 148;
+    MCQ_CUDA(cudaGetDevice(&dev));
+    MCQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int64_t need = (B + WPC16 - 1) / WPC16;
+    int64_t grid = (int64_t)sms * per_sm;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, WPC16 * 32, smem, st>>>(P, G, B, iters, idx_in, idx_out, work_counter);
+    MCQ_LAUNCH_CHECK("search2_kernel16");
+    return MCQ_OK;
+}
+
 
 template <int N>
 struct Launch2 {
@@ -544,7 +904,7 @@ int launch2(const float *P, const float *Gp, int64_t B, int iters, const int32_t
 
 }  // namespace
 
-bool search2_supports(int N, int K) { return K == 256 && (N == 2 || N == 4 || N == 8); }
+bool search2_supports(int N, int K) { return K == 256 && (N == 2 || N == 4 || N == 8 || N == 16); }
 
 int launch_search2(const float *P, const float *gram, int64_t B, int N, int K, int iters, const int32_t *idx_in,
                    int32_t *idx_out, cudaStream_t st, unsigned *work_counter) {
@@ -554,6 +914,7 @@ int launch_search2(const float *P, const float *gram, int64_t B, int N, int K, i
             case 2: return launch2<2>(P, gram, B, iters, idx_in, idx_out, st, work_counter);
             case 4: return launch2<4>(P, gram, B, iters, idx_in, idx_out, st, work_counter);
             case 8: return launch2<8>(P, gram, B, iters, idx_in, idx_out, st, work_counter);
+            case 16: return launch16(P, gram, B, iters, idx_in, idx_out, st, work_counter);
             default: break;
         }
     }

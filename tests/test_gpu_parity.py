@@ -120,7 +120,7 @@ def test_search_bit_exact_vs_model(golden_cases, name):
     assert nbad == 0, f"{nbad}/{len(ref)} frames differ from the bit-level model"
 
 
-@pytest.mark.parametrize("N,D,B", [(8, 512, 20000), (4, 256, 12000), (2, 128, 6000)])
+@pytest.mark.parametrize("N,D,B", [(16, 256, 6000), (8, 512, 20000), (4, 256, 12000), (2, 128, 6000)])
 @pytest.mark.parametrize("quantised", [False, True])
 def test_search_versions_agree(N, D, B, quantised):
     """The generic first-version kernel (MCQ_SEARCH=v1) and the K=256 kernel (search2.cu) are two implementations of
