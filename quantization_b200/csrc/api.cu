@@ -278,10 +278,21 @@ int mcq_encode(const void *x, int x_dtype, int64_t B, int D, int N, int K, const
         int32_t *idx = (int32_t *)(ws + W.off_idx);
         float *P = (float *)(ws + W.off_p);
         if ((rc = PROF(MCQ_PROF_OTHER, st, launch_split_x(xc, x_dtype, nb, L, blob, W, ws, true, st)))) return rc;
-        // classifier arg-max initialisation (quantization.py:297-301)
-        if ((rc = PROF(MCQ_PROF_GEMM, st, chunk_gemm(L, blob, W, ws, true, nb, st)))) return rc;
-        if ((rc = PROF(MCQ_PROF_OTHER, st, launch_argmax_init(P, (const float *)(blob + L.off_bias), nb, N, K, idx, st))))
-            return rc;
+        // classifier arg-max initialisation (quantization.py:297-301): fused into the GEMM epilogue when the tiles
+        // line up with the codebooks (MCQ_ARGMAX=unfused keeps the two-kernel path, for cross-checks)
+        const char *am = getenv("MCQ_ARGMAX");
+        if (use_tensor_core_gemm() && gemm_tc_argmax_supported(L.NK, K) && !(am && strcmp(am, "unfused") == 0)) {
+            if ((rc = PROF(MCQ_PROF_GEMM, st,
+                           launch_gemm_tc_argmax((const __nv_bfloat16 *)(ws + W.off_lsplit),
+                                                 (const __nv_bfloat16 *)(blob + L.off_wsplit), W.Mp, L.NK, L.Dp,
+                                                 (const float *)(blob + L.off_bias), nb, N, K, ws + W.off_p, idx, st))))
+                return rc;
+        } else {
+            if ((rc = PROF(MCQ_PROF_GEMM, st, chunk_gemm(L, blob, W, ws, true, nb, st)))) return rc;
+            if ((rc = PROF(MCQ_PROF_OTHER, st,
+                           launch_argmax_init(P, (const float *)(blob + L.off_bias), nb, N, K, idx, st))))
+                return rc;
+        }
         if (iters > 0) {
             if ((rc = PROF(MCQ_PROF_GEMM, st, chunk_gemm(L, blob, W, ws, false, nb, st)))) return rc;
             unsigned *ctr = (unsigned *)(ws + W.off_ctr);

@@ -73,6 +73,10 @@ int launch_gemm_ffma(const float *A, const float *Bm, float *C, int64_t M, int N
 // bf16x3 tcgen05 GEMM: C (M, NK) fp32 = sum of the six leading products of the split operands
 int launch_gemm_tc(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, float *C, int64_t Mp, int NK, int Dp,
                    cudaStream_t st);
+// logits GEMM with the classifier arg-max fused into the epilogue (K a multiple of 128); scratch: Mp * NK/128 * 8 bytes
+bool gemm_tc_argmax_supported(int NK, int K);
+int launch_gemm_tc_argmax(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, int64_t Mp, int NK, int Dp,
+                          const float *bias, int64_t B, int N, int K, void *scratch, int32_t *idx, cudaStream_t st);
 int launch_argmax_init(const float *logits, const float *bias, int64_t B, int N, int K, int32_t *idx, cudaStream_t st);
 // work_counter (optional, device, zeroed by the caller on `st`): lets the warps of the search kernel fetch frames
 // dynamically instead of striding over the batch (frames take 2..iters passes, so static striding leaves a tail)

@@ -112,11 +112,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ constexpr int kProdA[6] = {2, 1, 0, 1, 0, 0};
 __device__ constexpr int kProdB[6] = {0, 1, 2, 0, 1, 0};
 
-template <int BN>
+// ARGMAX: instead of storing the tile, the epilogue adds `bias` and keeps, per row, the first maximum of the tile's BN
+// columns: part_val / part_idx [row][n_tile] (the classifier arg-max of quantization.py:297-301 fused into the GEMM;
+// argmax_merge_kernel folds the K / BN tiles of a codebook).
+template <int BN, bool ARGMAX>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                    float *__restrict__ C, int m_tiles, int n_tiles, int k_blocks, int ldc, int a_plane_rows,
-                   int b_plane_rows) {
+                   int b_plane_rows, const float *__restrict__ bias, float *__restrict__ part_val,
+                   int *__restrict__ part_idx) {
     using Cfg = TcCfg<BN>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -234,6 +238,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             mbar_wait(tfull_bar(acc), aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float *crow = C + (size_t)(m0 + q * 32 + lane) * ldc + n0;
+            float best = 0.0f;
+            int bk = -1;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t r[32], rc[32];
@@ -241,15 +247,32 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 tmem_ld32(lane_base, r);
                 tmem_ld32(lane_base + (uint32_t)BN, rc);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if constexpr (ARGMAX) {
+                    const float *bs = bias + n0 + c * 32;
 #pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    float4 o;
-                    o.x = __uint_as_float(r[4 * v + 0]) + __uint_as_float(rc[4 * v + 0]);
-                    o.y = __uint_as_float(r[4 * v + 1]) + __uint_as_float(rc[4 * v + 1]);
-                    o.z = __uint_as_float(r[4 * v + 2]) + __uint_as_float(rc[4 * v + 2]);
-                    o.w = __uint_as_float(r[4 * v + 3]) + __uint_as_float(rc[4 * v + 3]);
-                    *reinterpret_cast<float4 *>(crow + c * 32 + 4 * v) = o;
+                    for (int v = 0; v < 32; ++v) {
+                        const float val = (__uint_as_float(r[v]) + __uint_as_float(rc[v])) + __ldg(bs + v);
+                        if (bk < 0 || val > best) {  // first maximum wins, like torch.argmax
+                            best = val;
+                            bk = n0 + c * 32 + v;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        float4 o;
+                        o.x = __uint_as_float(r[4 * v + 0]) + __uint_as_float(rc[4 * v + 0]);
+                        o.y = __uint_as_float(r[4 * v + 1]) + __uint_as_float(rc[4 * v + 1]);
+                        o.z = __uint_as_float(r[4 * v + 2]) + __uint_as_float(rc[4 * v + 2]);
+                        o.w = __uint_as_float(r[4 * v + 3]) + __uint_as_float(rc[4 * v + 3]);
+                        *reinterpret_cast<float4 *>(crow + c * 32 + 4 * v) = o;
+                    }
                 }
+            }
+            if constexpr (ARGMAX) {
+                const size_t slot = (size_t)(m0 + q * 32 + lane) * n_tiles + (n0 / BN);
+                part_val[slot] = best;
+                part_idx[slot] = bk;
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -307,16 +330,16 @@ int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint
     return MCQ_OK;
 }
 
-template <int BN>
+template <int BN, bool ARGMAX>
 int launch_bn(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, float *C, int64_t Mp, int NK, int Dp,
-              cudaStream_t st) {
+              cudaStream_t st, const float *bias = nullptr, float *part_val = nullptr, int *part_idx = nullptr) {
     using Cfg = TcCfg<BN>;
     const uint64_t NKp = align_up((size_t)NK, 128);
     CUtensorMap ma, mb;
     int rc;
     if ((rc = make_map(&ma, a_split, 3ull * (uint64_t)Mp, (uint64_t)Dp, BM))) return rc;
     if ((rc = make_map(&mb, b_split, 3ull * NKp, (uint64_t)Dp, BN))) return rc;
-    auto kern = gemm_bf16x3_kernel<BN>;
+    auto kern = gemm_bf16x3_kernel<BN, ARGMAX>;
     MCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     int dev = 0, sms = 148;
     MCQ_CUDA(cudaGetDevice(&dev));
@@ -324,7 +347,8 @@ int launch_bn(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, float 
     const int m_tiles = (int)(Mp / BM), n_tiles = NK / BN;
     int64_t tiles = (int64_t)m_tiles * n_tiles;
     int grid = (int)(tiles < sms ? tiles : sms);
-    kern<<<grid, NUM_THREADS, Cfg::SMEM, st>>>(ma, mb, C, m_tiles, n_tiles, Dp / BK, NK, (int)Mp, (int)NKp);
+    kern<<<grid, NUM_THREADS, Cfg::SMEM, st>>>(ma, mb, C, m_tiles, n_tiles, Dp / BK, NK, (int)Mp, (int)NKp, bias, part_val,
+                                               part_idx);
     MCQ_LAUNCH_CHECK("gemm_bf16x3_kernel");
     return MCQ_OK;
 }
@@ -338,8 +362,52 @@ int launch_gemm_tc(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, f
         set_error("gemm_tc: Mp=%lld Dp=%d NK=%d not tile aligned", (long long)Mp, Dp, NK);
         return MCQ_EINVAL;
     }
-    if (NK % 128 == 0) return launch_bn<128>(a_split, b_split, C, Mp, NK, Dp, st);
-    return launch_bn<64>(a_split, b_split, C, Mp, NK, Dp, st);
+    if (NK % 128 == 0) return launch_bn<128, false>(a_split, b_split, C, Mp, NK, Dp, st);
+    return launch_bn<64, false>(a_split, b_split, C, Mp, NK, Dp, st);
+}
+
+// idx[b][n] = first maximum over the K / 128 tile maxima of codebook n (ascending tile = ascending column order)
+__global__ void argmax_merge_kernel(const float *__restrict__ part_val, const int *__restrict__ part_idx, int64_t B,
+                                    int N, int K, int n_tiles, int32_t *__restrict__ idx) {
+    const int tpc = K / 128;  // tiles per codebook
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B * N; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / N;
+        const int n = (int)(i - b * N);
+        const size_t base = (size_t)b * n_tiles + (size_t)n * tpc;
+        float best = part_val[base];
+        int bk = part_idx[base];
+        for (int t = 1; t < tpc; ++t) {
+            const float v = part_val[base + t];
+            if (v > best) {
+                best = v;
+                bk = part_idx[base + t];
+            }
+        }
+        idx[i] = bk - n * K;
+    }
+}
+
+bool gemm_tc_argmax_supported(int NK, int K) { return NK % 128 == 0 && K % 128 == 0; }
+
+// logits GEMM with the classifier arg-max fused into its epilogue: idx (B, N) int32.  `scratch` holds
+// Mp * (NK / 128) * 8 bytes of per-tile maxima.
+int launch_gemm_tc_argmax(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, int64_t Mp, int NK, int Dp,
+                          const float *bias, int64_t B, int N, int K, void *scratch, int32_t *idx, cudaStream_t st) {
+    if (Mp <= 0) return MCQ_OK;
+    if (Mp % BM != 0 || Dp % BK != 0 || !gemm_tc_argmax_supported(NK, K)) {
+        set_error("gemm_tc_argmax: Mp=%lld Dp=%d NK=%d K=%d not supported", (long long)Mp, Dp, NK, K);
+        return MCQ_EINVAL;
+    }
+    const int n_tiles = NK / 128;
+    float *part_val = (float *)scratch;
+    int *part_idx = (int *)(part_val + (size_t)Mp * n_tiles);
+    int rc = launch_bn<128, true>(a_split, b_split, nullptr, Mp, NK, Dp, st, bias, part_val, part_idx);
+    if (rc) return rc;
+    int64_t blocks = (B * N + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    argmax_merge_kernel<<<(unsigned)blocks, 256, 0, st>>>(part_val, part_idx, B, N, K, n_tiles, idx);
+    MCQ_LAUNCH_CHECK("argmax_merge_kernel");
+    return MCQ_OK;
 }
 
 }  // namespace mcq
