@@ -35,15 +35,9 @@ __device__ __forceinline__ float credux_min(float v) {
     return m;
 }
 
-// Scattered 4-byte reads of G (element offsets).  A texture-object variant of these gathers (TEX data pipe instead of
-// the LSU pipe) was measured and is slower (9.3 ms vs 7.2 ms per 75,776 frames, profiles/r01_search2.md), so it is gone.
-struct GSrc {
-    const float *g;
-};
-template <bool TEX>
-__device__ __forceinline__ float gat(const GSrc &G, unsigned idx) {
-    return __ldg(G.g + idx);
-}
+// Scattered 4-byte read of G (element offset).  A texture-object variant of these gathers (TEX data pipe instead of
+// the LSU pipe) was measured and is slower (9.3 ms vs 7.2 ms per 75,776 frames, profiles/r01_search2.md).
+__device__ __forceinline__ float gat(const float *__restrict__ G, unsigned idx) { return __ldg(G + idx); }
 
 // (a0, a1) += (b0, b1): one FADD2 (packed fp32 add, each half an IEEE round-to-nearest add)
 __device__ __forceinline__ void fadd2(float &a0, float &a1, float b0, float b1) {
@@ -201,8 +195,8 @@ __device__ __forceinline__ void level1(Mem &s, const float *__restrict__ Pb, con
     }
 }
 
-template <int N, bool TEX>
-__device__ __forceinline__ void gather_uv(WarpMem2<N> &s, const GSrc &G, int lane) {
+template <int N>
+__device__ __forceinline__ void gather_uv(WarpMem2<N> &s, const float *__restrict__ G, int lane) {
     const int p = lane & 15, mh = lane >> 4;
     unsigned ro[N / 2];
 #pragma unroll
@@ -215,7 +209,7 @@ __device__ __forceinline__ void gather_uv(WarpMem2<N> &s, const GSrc &G, int lan
         for (int aa = 0; aa < AB; ++aa) {
             const unsigned col = (a0 + aa) * K2 + s.kk[a0 + aa][p];
 #pragma unroll
-            for (int r = 0; r < N / 2; ++r) val[aa][r] = gat<TEX>(G, ro[r] + col);  // (m == a is read but not used)
+            for (int r = 0; r < N / 2; ++r) val[aa][r] = gat(G, ro[r] + col);  // (m == a is read but not used)
         }
 #pragma unroll
         for (int aa = 0; aa < AB; ++aa)
@@ -227,14 +221,14 @@ __device__ __forceinline__ void gather_uv(WarpMem2<N> &s, const GSrc &G, int lan
 
 // Merge of two single codebooks e = 2g, o = 2g+1: 16 x 16 joint candidates (quantization.py:504-547 at L = 1).
 // Lane (hi, j) scores candidates (i = 8*hi + t, j), t = 0..7: a request reads two G rows x 16 columns.
-template <int N, bool TEX, bool FINAL>
-__device__ __forceinline__ void merge1(WarpMem2<N> &s, const GSrc &G, int g, int lane) {
+template <int N, bool FINAL>
+__device__ __forceinline__ void merge1(WarpMem2<N> &s, const float *__restrict__ G, int g, int lane) {
     const int e = 2 * g, o = e + 1;
     const int j = lane & 15, ib = (lane >> 4) * 8;
     const unsigned ko = o * K2 + s.kk[o][j];
     const float v = s.uv[o][e][j];
     const float kdo = s.kd1[o][j];
-    const float w = gat<TEX>(G, s.rowoff[e] + o * K2 + s.old[o]);
+    const float w = gat(G, s.rowoff[e] + o * K2 + s.old[o]);
     unsigned rowp[8];
     float u[8], kde[8];
     {
@@ -251,7 +245,7 @@ __device__ __forceinline__ void merge1(WarpMem2<N> &s, const GSrc &G, int g, int
     }
     float gv[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) gv[t] = gat<TEX>(G, rowp[t] + ko);
+    for (int t = 0; t < 8; ++t) gv[t] = gat(G, rowp[t] + ko);
     float key[8];
     int flat[8];
 #pragma unroll
@@ -282,8 +276,8 @@ __device__ __forceinline__ void merge1(WarpMem2<N> &s, const GSrc &G, int g, int
 
 // Merge of two codebook pairs: groups e = 2g (codebooks 4g, 4g+1) and o = 2g+1 (4g+2, 4g+3), 16 x 16 candidates.
 // Same lane mapping as merge1: lane (hi, j) scores (i = 8*hi + t, j).
-template <int N, bool TEX, bool FINAL>
-__device__ __forceinline__ void merge2(WarpMem2<N> &s, const GSrc &G, int g, int lane) {
+template <int N, bool FINAL>
+__device__ __forceinline__ void merge2(WarpMem2<N> &s, const float *__restrict__ G, int g, int lane) {
     const int e = 2 * g, o = e + 1;
     const int a0 = 4 * g, a1 = a0 + 1, b0 = a0 + 2, b1 = a0 + 3;
     const int j = lane & 15, ib = (lane >> 4) * 8;
@@ -293,8 +287,8 @@ __device__ __forceinline__ void merge2(WarpMem2<N> &s, const GSrc &G, int g, int
     const float v00 = s.uv[b0][a0][q0], v10 = s.uv[b0][a1][q0], v01 = s.uv[b1][a0][q1], v11 = s.uv[b1][a1][q1];
     const float kdo = s.kd2[o][j];
     const unsigned cb0 = b0 * K2 + s.old[b0], cb1 = b1 * K2 + s.old[b1];
-    const float w00 = gat<TEX>(G, s.rowoff[a0] + cb0), w10 = gat<TEX>(G, s.rowoff[a1] + cb0);
-    const float w01 = gat<TEX>(G, s.rowoff[a0] + cb1), w11 = gat<TEX>(G, s.rowoff[a1] + cb1);
+    const float w00 = gat(G, s.rowoff[a0] + cb0), w10 = gat(G, s.rowoff[a1] + cb0);
+    const float w01 = gat(G, s.rowoff[a0] + cb1), w11 = gat(G, s.rowoff[a1] + cb1);
     unsigned tis[8];
     float kde[8];
     {
@@ -310,10 +304,10 @@ __device__ __forceinline__ void merge2(WarpMem2<N> &s, const GSrc &G, int g, int
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
         const unsigned rp0 = s.rowk[a0][tis[t] & 15], rp1 = s.rowk[a1][tis[t] >> 4];
-        g00[t] = gat<TEX>(G, rp0 + c0);
-        g10[t] = gat<TEX>(G, rp1 + c0);
-        g01[t] = gat<TEX>(G, rp0 + c1);
-        g11[t] = gat<TEX>(G, rp1 + c1);
+        g00[t] = gat(G, rp0 + c0);
+        g10[t] = gat(G, rp1 + c0);
+        g01[t] = gat(G, rp0 + c1);
+        g11[t] = gat(G, rp1 + c1);
     }
     float key[8];
     int flat[8];
@@ -354,8 +348,8 @@ __device__ __forceinline__ void merge2(WarpMem2<N> &s, const GSrc &G, int g, int
 }
 
 // Final merge of two codebook quads (N = 8): 32 x 32 joint candidates, candidate flat = i*32 + j.
-template <int N, bool TEX>
-__device__ __forceinline__ void merge4_final(WarpMem2<N> &s, const GSrc &G, int lane) {
+template <int N>
+__device__ __forceinline__ void merge4_final(WarpMem2<N> &s, const float *__restrict__ G, int lane) {
     const unsigned ti = s.kt3[0][lane];  // as row i = lane: my slots of codebooks 0..3
     const unsigned tj = s.kt3[1][lane];  // as column j = lane: my slots of codebooks 4..7
 #pragma unroll
@@ -399,10 +393,10 @@ __device__ __forceinline__ void merge4_final(WarpMem2<N> &s, const GSrc &G, int 
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 gv[t] = 0.0f;
-                if ((msk >> t) & 1u) gv[t] = gat<TEX>(G, ra[t] + cq);
+                if ((msk >> t) & 1u) gv[t] = gat(G, ra[t] + cq);
             }
             const float v = s.uv[b][a][q];
-            const float w = gat<TEX>(G, s.rowoff[a] + cbo);
+            const float w = gat(G, s.rowoff[a] + cbo);
 #pragma unroll
             for (int t = 0; t < 8; ++t) s.tab[trow_off(pb + t) + q] = ((gv[t] - u[t]) - v) + w;
             __syncwarp();
@@ -448,23 +442,23 @@ __device__ __forceinline__ void merge4_final(WarpMem2<N> &s, const GSrc &G, int 
     __syncwarp();
 }
 
-template <int N, bool TEX>
-__device__ __forceinline__ void refine_pass2(WarpMem2<N> &s, const float *__restrict__ Pb, const GSrc &G, int lane) {
+template <int N>
+__device__ __forceinline__ void refine_pass2(WarpMem2<N> &s, const float *__restrict__ Pb, const float *__restrict__ G, int lane) {
     if (lane < N) s.rowoff[lane] = (unsigned)(lane * K2 + s.old[lane]) * (unsigned)(N * K2);
     __syncwarp();
-    level1<N, WarpMem2<N>>(s, Pb, G.g, lane);
-    gather_uv<N, TEX>(s, G, lane);
+    level1<N, WarpMem2<N>>(s, Pb, G, lane);
+    gather_uv<N>(s, G, lane);
     if constexpr (N == 2) {
-        merge1<N, TEX, true>(s, G, 0, lane);
+        merge1<N, true>(s, G, 0, lane);
     } else {
 #pragma unroll 1
-        for (int g = 0; g < N / 2; ++g) merge1<N, TEX, false>(s, G, g, lane);
+        for (int g = 0; g < N / 2; ++g) merge1<N, false>(s, G, g, lane);
         if constexpr (N == 4) {
-            merge2<N, TEX, true>(s, G, 0, lane);
+            merge2<N, true>(s, G, 0, lane);
         } else {
 #pragma unroll 1
-            for (int g = 0; g < N / 4; ++g) merge2<N, TEX, false>(s, G, g, lane);
-            merge4_final<N, TEX>(s, G, lane);
+            for (int g = 0; g < N / 4; ++g) merge2<N, false>(s, G, g, lane);
+            merge4_final<N>(s, G, lane);
         }
     }
 }
@@ -504,7 +498,7 @@ struct alignas(16) WarpMem16 {
 // ul/vl of the NA x NB codebook pairs (a_base + la, b_base + lb), pair index c = la * NB + lb.
 // Lanes 0..15 fetch u (slot p = lane), lanes 16..31 fetch v (slot q = lane - 16).
 template <int NA, int NB>
-__device__ __forceinline__ void gather_uv_local(WarpMem16 &s, const GSrc &G, int a_base, int b_base, int lane) {
+__device__ __forceinline__ void gather_uv_local(WarpMem16 &s, const float *__restrict__ G, int a_base, int b_base, int lane) {
     const int sl = lane & 15;
     const bool isv = lane >= 16;
     constexpr int NC = NA * NB;
@@ -518,7 +512,7 @@ __device__ __forceinline__ void gather_uv_local(WarpMem16 &s, const GSrc &G, int
             const int a = a_base + c / NB, b = b_base + c % NB;
             // u: row of (b, old_b), column (a, kk_a[p]);  v: row of (a, old_a), column (b, kk_b[q])
             const unsigned idx = isv ? s.rowoff[a] + b * K2 + s.kk[b][sl] : s.rowoff[b] + a * K2 + s.kk[a][sl];
-            val[cc] = gat<false>(G, idx);
+            val[cc] = gat(G, idx);
         }
 #pragma unroll
         for (int cc = 0; cc < BATCH; ++cc) {
@@ -531,19 +525,19 @@ __device__ __forceinline__ void gather_uv_local(WarpMem16 &s, const GSrc &G, int
     __syncwarp();
 }
 
-__device__ __forceinline__ void merge1_16(WarpMem16 &s, const GSrc &G, int g, int lane) {
+__device__ __forceinline__ void merge1_16(WarpMem16 &s, const float *__restrict__ G, int g, int lane) {
     const int e = 2 * g, o = e + 1;
     gather_uv_local<1, 1>(s, G, e, o, lane);
     const int j = lane & 15, ib = (lane >> 4) * 8;
     const unsigned ko = o * K2 + s.kk[o][j];
     const float v = s.vl[0][j];
     const float kdo = s.kd1[o][j];
-    const float w = gat<false>(G, s.rowoff[e] + o * K2 + s.old[o]);
+    const float w = gat(G, s.rowoff[e] + o * K2 + s.old[o]);
     float key[8];
     int flat[8];
     float gv[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) gv[t] = gat<false>(G, s.rowk[e][ib + t] + ko);
+    for (int t = 0; t < 8; ++t) gv[t] = gat(G, s.rowk[e][ib + t] + ko);
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
         const float d = ((gv[t] - s.ul[0][ib + t]) - v) + w;
@@ -560,7 +554,7 @@ __device__ __forceinline__ void merge1_16(WarpMem16 &s, const GSrc &G, int g, in
     __syncwarp();
 }
 
-__device__ __forceinline__ void merge2_16(WarpMem16 &s, const GSrc &G, int g, int lane) {
+__device__ __forceinline__ void merge2_16(WarpMem16 &s, const float *__restrict__ G, int g, int lane) {
     const int e = 2 * g, o = e + 1;
     const int a0 = 4 * g, a1 = a0 + 1, b0 = a0 + 2, b1 = a0 + 3;
     gather_uv_local<2, 2>(s, G, a0, b0, lane);  // pair index c = la * 2 + lb
@@ -571,18 +565,18 @@ __device__ __forceinline__ void merge2_16(WarpMem16 &s, const GSrc &G, int g, in
     const float v00 = s.vl[0][q0], v10 = s.vl[2][q0], v01 = s.vl[1][q1], v11 = s.vl[3][q1];
     const float kdo = s.kd2[o][j];
     const unsigned cb0 = b0 * K2 + s.old[b0], cb1 = b1 * K2 + s.old[b1];
-    const float w00 = gat<false>(G, s.rowoff[a0] + cb0), w10 = gat<false>(G, s.rowoff[a1] + cb0);
-    const float w01 = gat<false>(G, s.rowoff[a0] + cb1), w11 = gat<false>(G, s.rowoff[a1] + cb1);
+    const float w00 = gat(G, s.rowoff[a0] + cb0), w10 = gat(G, s.rowoff[a1] + cb0);
+    const float w01 = gat(G, s.rowoff[a0] + cb1), w11 = gat(G, s.rowoff[a1] + cb1);
     float g00[8], g10[8], g01[8], g11[8];
     unsigned tis[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
         tis[t] = s.kt2[e][ib + t];
         const unsigned rp0 = s.rowk[a0][tis[t] & 15], rp1 = s.rowk[a1][tis[t] >> 4];
-        g00[t] = gat<false>(G, rp0 + c0);
-        g10[t] = gat<false>(G, rp1 + c0);
-        g01[t] = gat<false>(G, rp0 + c1);
-        g11[t] = gat<false>(G, rp1 + c1);
+        g00[t] = gat(G, rp0 + c0);
+        g10[t] = gat(G, rp1 + c0);
+        g01[t] = gat(G, rp0 + c1);
+        g11[t] = gat(G, rp1 + c1);
     }
     float key[8];
     int flat[8];
@@ -611,7 +605,7 @@ __device__ __forceinline__ void merge2_16(WarpMem16 &s, const GSrc &G, int g, in
 // dot(i, j) of the 32 x 32 joint candidates of two groups of NA codebooks each (a_base.., b_base..), lane = column j,
 // dot[i] over the rows i.  ti / tj: this lane's slot tuple as row i = lane / as column j = lane (4 bits per codebook).
 template <int NA>
-__device__ __forceinline__ void wide_dots(WarpMem16 &s, const GSrc &G, int a_base, int b_base, unsigned ti, unsigned tj,
+__device__ __forceinline__ void wide_dots(WarpMem16 &s, const float *__restrict__ G, int a_base, int b_base, unsigned ti, unsigned tj,
                                           int lane, float (&dot)[32]) {
 #pragma unroll
     for (int c = 0; c < NA; ++c) {
@@ -656,10 +650,10 @@ __device__ __forceinline__ void wide_dots(WarpMem16 &s, const GSrc &G, int a_bas
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 gv[t] = 0.0f;
-                if ((msk >> t) & 1u) gv[t] = gat<false>(G, ra[t] + cq);
+                if ((msk >> t) & 1u) gv[t] = gat(G, ra[t] + cq);
             }
             const float v = s.vl[c][q];
-            const float w = gat<false>(G, s.rowoff[a] + cbo);
+            const float w = gat(G, s.rowoff[a] + cbo);
 #pragma unroll
             for (int t = 0; t < 8; ++t) s.tab[trow_off(pb + t) + q] = ((gv[t] - u[t]) - v) + w;
             __syncwarp();
@@ -687,7 +681,7 @@ __device__ __forceinline__ void wide_dots(WarpMem16 &s, const GSrc &G, int a_bas
 
 // Quad merge of N = 16 (not final): groups e = 2g (codebooks 8g..8g+3) and o = 2g+1 (8g+4..8g+7); keeps the 32 best
 // of the 1024 joint candidates, ascending by (score, flat = i*32 + j).
-__device__ __forceinline__ void merge4_16(WarpMem16 &s, const GSrc &G, int g, int lane) {
+__device__ __forceinline__ void merge4_16(WarpMem16 &s, const float *__restrict__ G, int g, int lane) {
     const int e = 2 * g, o = e + 1;
     const unsigned ti = s.kt3[e][lane], tj = s.kt3[o][lane];
     float dot[32];
@@ -733,7 +727,7 @@ __device__ __forceinline__ void merge4_16(WarpMem16 &s, const GSrc &G, int g, in
 }
 
 // Final merge of N = 16: the two octets, 32 x 32 candidates, best one wins.
-__device__ __forceinline__ void merge8_final_16(WarpMem16 &s, const GSrc &G, int lane) {
+__device__ __forceinline__ void merge8_final_16(WarpMem16 &s, const float *__restrict__ G, int lane) {
     const unsigned ti = s.kt4[0][lane], tj = s.kt4[1][lane];
     float dot[32];
     wide_dots<8>(s, G, 0, 8, ti, tj, lane, dot);
@@ -760,10 +754,10 @@ __device__ __forceinline__ void merge8_final_16(WarpMem16 &s, const GSrc &G, int
     __syncwarp();
 }
 
-__device__ __forceinline__ void refine_pass16(WarpMem16 &s, const float *__restrict__ Pb, const GSrc &G, int lane) {
+__device__ __forceinline__ void refine_pass16(WarpMem16 &s, const float *__restrict__ Pb, const float *__restrict__ G, int lane) {
     if (lane < 16) s.rowoff[lane] = (unsigned)(lane * K2 + s.old[lane]) * (unsigned)(16 * K2);
     __syncwarp();
-    level1<16, WarpMem16>(s, Pb, G.g, lane);
+    level1<16, WarpMem16>(s, Pb, G, lane);
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) merge1_16(s, G, g, lane);
 #pragma unroll 1
@@ -776,7 +770,7 @@ __device__ __forceinline__ void refine_pass16(WarpMem16 &s, const float *__restr
 constexpr int WPC16 = 4;
 
 __global__ void __launch_bounds__(WPC16 * 32, 4)
-    search2_kernel16(const float *__restrict__ P, GSrc G, int64_t B, int iters, const int32_t *__restrict__ idx_in,
+    search2_kernel16(const float *__restrict__ P, const float *__restrict__ G, int64_t B, int iters, const int32_t *__restrict__ idx_in,
                      int32_t *__restrict__ idx_out, unsigned *__restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -810,7 +804,7 @@ __global__ void __launch_bounds__(WPC16 * 32, 4)
 
 int launch16(const float *P, const float *Gp, int64_t B, int iters, const int32_t *idx_in, int32_t *idx_out,
              cudaStream_t st, unsigned *work_counter) {
-    GSrc G{Gp};
+    const float *G = Gp;
     const size_t smem = sizeof(WarpMem16) * WPC16;
     auto kern = search2_kernel16;
     MCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -835,9 +829,9 @@ struct Launch2 {
     static constexpr int WPC = (N == 8) ? MCQ_S2_WPC : 8;  // warps per CTA
 };
 
-template <int N, bool TEX>
+template <int N>
 __global__ void __launch_bounds__(Launch2<N>::WPC * 32, (N == 8 ? 4 : 3))
-    search2_kernel(const float *__restrict__ P, GSrc G, int64_t B, int iters, const int32_t *__restrict__ idx_in,
+    search2_kernel(const float *__restrict__ P, const float *__restrict__ G, int64_t B, int iters, const int32_t *__restrict__ idx_in,
                    int32_t *__restrict__ idx_out, unsigned *__restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -856,7 +850,7 @@ __global__ void __launch_bounds__(Launch2<N>::WPC * 32, (N == 8 ? 4 : 3))
 #pragma unroll 1
         for (int it = 0; it < iters; ++it) {
             const int prev = (lane < N) ? s.old[lane] : 0;
-            refine_pass2<N, TEX>(s, Pb, G, lane);
+            refine_pass2<N>(s, Pb, G, lane);
             const int now = (lane < N) ? s.old[lane] : 0;
             // a pass that returns its input is a fixed point of a deterministic map: the remaining passes are no-ops
             if (__all_sync(FULL, prev == now)) break;
@@ -873,12 +867,12 @@ __global__ void __launch_bounds__(Launch2<N>::WPC * 32, (N == 8 ? 4 : 3))
     }
 }
 
-template <int N, bool TEX>
-int launch2t(const float *P, const GSrc &G, int64_t B, int iters, const int32_t *idx_in, int32_t *idx_out,
+template <int N>
+int launch2t(const float *P, const float *G, int64_t B, int iters, const int32_t *idx_in, int32_t *idx_out,
              cudaStream_t st, unsigned *work_counter) {
     constexpr int wpc = Launch2<N>::WPC;
     const size_t smem = sizeof(WarpMem2<N>) * wpc;
-    auto kern = search2_kernel<N, TEX>;
+    auto kern = search2_kernel<N>;
     MCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     MCQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
@@ -898,8 +892,7 @@ int launch2t(const float *P, const GSrc &G, int64_t B, int iters, const int32_t 
 template <int N>
 int launch2(const float *P, const float *Gp, int64_t B, int iters, const int32_t *idx_in, int32_t *idx_out,
             cudaStream_t st, unsigned *work_counter) {
-    GSrc G{Gp};
-    return launch2t<N, false>(P, G, B, iters, idx_in, idx_out, st, work_counter);
+    return launch2t<N>(P, Gp, B, iters, idx_in, idx_out, st, work_counter);
 }
 
 }  // namespace
