@@ -55,8 +55,10 @@ Prepared prepared_layout(int N, int K, int D) {
     L.off_bias = take(sizeof(float) * (size_t)L.NK);
     L.off_gram = take(sizeof(float) * ((size_t)L.NK * L.NK + L.NK));  // table followed by its diagonal
     L.off_scal = take(sizeof(float) * 4);
-    L.off_csplit = take(sizeof(__nv_bfloat16) * 3 * NKp * L.Dp);
-    L.off_wsplit = take(sizeof(__nv_bfloat16) * 3 * NKp * L.Dp);
+    L.off_csplit = take(sizeof(__half) * 2 * NKp * L.Dp);
+    L.off_wsplit = take(sizeof(__half) * 2 * NKp * L.Dp);
+    L.off_cscale = take(sizeof(float) * NKp);
+    L.off_wscale = take(sizeof(float) * NKp);
     L.bytes = off;
     return L;
 }
@@ -69,8 +71,10 @@ Workspace workspace_layout(int64_t Bc, int N, int K, int D) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
     W.off_xf = take(sizeof(float) * (size_t)W.Mp * D);
-    W.off_xsplit = take(sizeof(__nv_bfloat16) * 3 * (size_t)W.Mp * Dp);
-    W.off_lsplit = take(sizeof(__nv_bfloat16) * 3 * (size_t)W.Mp * Dp);
+    W.off_xsplit = take(sizeof(__half) * 2 * (size_t)W.Mp * Dp);
+    W.off_lsplit = take(sizeof(__half) * 2 * (size_t)W.Mp * Dp);
+    W.off_xscale = take(sizeof(float) * (size_t)W.Mp);
+    W.off_lscale = take(sizeof(float) * (size_t)W.Mp);
     W.off_p = take(sizeof(float) * (size_t)W.Mp * NK);
     W.off_idx = take(sizeof(int32_t) * (size_t)W.Mp * N);
     W.off_ctr = take(1024);
@@ -107,15 +111,17 @@ bool use_tensor_core_gemm() {
     return !(e && strcmp(e, "ffma") == 0);
 }
 
-// P-like GEMM of one chunk: out (Mp, NK) = A . Bm^T, either through the tcgen05 bf16x3 kernel or the FFMA kernel.
+// P-like GEMM of one chunk: out (Mp, NK) = A . Bm^T, either through the tcgen05 fp16x2 kernel or the FFMA kernel.
 static int chunk_gemm(const Prepared &L, const char *blob, const Workspace &W, char *ws, bool logits, int64_t Bc,
                       cudaStream_t st) {
     float *out = (float *)(ws + W.off_p);
     const bool tc = use_tensor_core_gemm() && L.NK % 64 == 0;
     if (tc) {
-        const __nv_bfloat16 *a = (const __nv_bfloat16 *)(ws + (logits ? W.off_lsplit : W.off_xsplit));
-        const __nv_bfloat16 *b = (const __nv_bfloat16 *)(blob + (logits ? L.off_wsplit : L.off_csplit));
-        return launch_gemm_tc(a, b, out, W.Mp, L.NK, L.Dp, st);
+        const __half *a = (const __half *)(ws + (logits ? W.off_lsplit : W.off_xsplit));
+        const __half *b = (const __half *)(blob + (logits ? L.off_wsplit : L.off_csplit));
+        const float *as = (const float *)(ws + (logits ? W.off_lscale : W.off_xscale));
+        const float *bs = (const float *)(blob + (logits ? L.off_wscale : L.off_cscale));
+        return launch_gemm_tc(a, as, b, bs, out, W.Mp, L.NK, L.Dp, st);
     }
     const float *a = (const float *)(ws + W.off_xf);
     const float *b = (const float *)(blob + (logits ? L.off_w : L.off_cs));
@@ -283,8 +289,10 @@ int mcq_encode(const void *x, int x_dtype, int64_t B, int D, int N, int K, const
         const char *am = getenv("MCQ_ARGMAX");
         if (use_tensor_core_gemm() && gemm_tc_argmax_supported(L.NK, K) && !(am && strcmp(am, "unfused") == 0)) {
             if ((rc = PROF(MCQ_PROF_GEMM, st,
-                           launch_gemm_tc_argmax((const __nv_bfloat16 *)(ws + W.off_lsplit),
-                                                 (const __nv_bfloat16 *)(blob + L.off_wsplit), W.Mp, L.NK, L.Dp,
+                           launch_gemm_tc_argmax((const __half *)(ws + W.off_lsplit),
+                                                 (const float *)(ws + W.off_lscale),
+                                                 (const __half *)(blob + L.off_wsplit),
+                                                 (const float *)(blob + L.off_wscale), W.Mp, L.NK, L.Dp,
                                                  (const float *)(blob + L.off_bias), nb, N, K, ws + W.off_p, idx, st))))
                 return rc;
         } else {
@@ -436,8 +444,9 @@ int mcq_class_loss_forward(const void *x, int x_dtype, int64_t B, int D, int N, 
         if (tc) {
             const int64_t mp = (int64_t)align_up((size_t)nb, 128);
             rc = PROF(MCQ_PROF_GEMM, st,
-                      launch_gemm_tc((const __nv_bfloat16 *)(ws + W.off_lsplit),
-                                     (const __nv_bfloat16 *)(blob + L.off_wsplit), out, mp, L.NK, L.Dp, st));
+                      launch_gemm_tc((const __half *)(ws + W.off_lsplit), (const float *)(ws + W.off_lscale),
+                                     (const __half *)(blob + L.off_wsplit), (const float *)(blob + L.off_wscale), out,
+                                     mp, L.NK, L.Dp, st));
         } else {
             rc = PROF(MCQ_PROF_GEMM, st,
                       launch_gemm_ffma((const float *)(ws + W.off_xf), (const float *)(blob + L.off_w), out, nb, L.NK,

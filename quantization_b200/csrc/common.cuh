@@ -31,14 +31,16 @@ static inline bool is_pow2(long v) { return v > 0 && (v & (v - 1)) == 0; }
 // Layout of the caller-owned prepared blob (device memory).  All offsets are multiples of 1024 bytes.
 struct Prepared {
     int N, K, D, NK;
-    int Dp;  // D rounded up to a multiple of 64: row length of the bf16 split operands
+    int Dp;  // D rounded up to a multiple of 64: row length of the fp16 split operands
     size_t off_cs;     // float [NK*D]   scaled centers  exp(centers_scale*speed) * centers   (quantization.py:77-79)
     size_t off_w;      // float [NK*D]   to_logits.weight (copy)
     size_t off_bias;   // float [NK]     to_logits.bias (copy)
     size_t off_gram;   // float [NK*NK]  G = Cs Cs^T (fp64 accumulation, rounded once)
     size_t off_scal;   // float [4]      {centers scale, logits scale}
-    size_t off_csplit; // bf16  [3][NK*Dp] three-way bf16 split of cs (operands of the tcgen05 GEMM)
-    size_t off_wsplit; // bf16  [3][NK*Dp] three-way bf16 split of w
+    size_t off_csplit; // half  [2][NKp*Dp] two-way fp16 split of the row-scaled cs (operands of the tcgen05 GEMM)
+    size_t off_wsplit; // half  [2][NKp*Dp] two-way fp16 split of the row-scaled w
+    size_t off_cscale; // float [NKp]  2^-e of each cs row (the GEMM epilogue multiplies by it)
+    size_t off_wscale; // float [NKp]  ... of each w row
     size_t bytes;
 };
 
@@ -49,8 +51,10 @@ struct Workspace {
     int64_t Bc;
     int Mp;            // Bc rounded up to 128
     size_t off_xf;     // float [Mp*D]      x as fp32 (identity for fp32 input is still copied: uniform path)
-    size_t off_xsplit; // bf16  [3][Mp*Dp]  split of x
-    size_t off_lsplit; // bf16  [3][Mp*Dp]  split of fl(logits_scale * x)
+    size_t off_xsplit; // half  [2][Mp*Dp]  two-way fp16 split of the row-scaled x
+    size_t off_lsplit; // half  [2][Mp*Dp]  ... of the row-scaled fl(logits_scale * x)
+    size_t off_xscale; // float [Mp]  2^-e of each x row
+    size_t off_lscale; // float [Mp]  ... of each fl(logits_scale * x) row
     size_t off_p;      // float [Mp*NK]     P = x Cs^T   (also receives the logits before P is formed)
     size_t off_idx;    // int32 [Mp*N]
     size_t off_ctr;    // uint32 [256]      work counter of the search kernel (dynamic frame scheduling)
@@ -64,19 +68,20 @@ int check_shape(int N, int K, int D);
 // ---- kernel launchers (each enqueues on `st` and returns MCQ_OK or an error) -------------------------------------
 int launch_prepare(const float *centers, const float *centers_scale, const float *w, const float *bias,
                    const float *logits_scale, float scale_speed, const Prepared &L, char *blob, cudaStream_t st);
-// x (any dtype) -> fp32 copy, bf16 splits of x and of fl(lscale * x)
+// x (any dtype) -> fp32 copy, row-scaled fp16 splits of x and of fl(lscale * x)
 int launch_split_x(const void *x, int x_dtype, int64_t B, const Prepared &L, const char *blob, const Workspace &W,
                    char *ws, bool want_logits_split, cudaStream_t st);
 // C (M, NK) = A (M, D) . Bm (NK, D)^T  plain fp32 FFMA version (scaffolding / cross-check of the tcgen05 GEMM)
 int launch_gemm_ffma(const float *A, const float *Bm, float *C, int64_t M, int NK, int D, const float *a_scale,
                      cudaStream_t st);
-// bf16x3 tcgen05 GEMM: C (M, NK) fp32 = sum of the six leading products of the split operands
-int launch_gemm_tc(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, float *C, int64_t Mp, int NK, int Dp,
-                   cudaStream_t st);
+// fp16x2 tcgen05 GEMM: C (M, NK) fp32 = (a0 b0 + a0 b1 + a1 b0) * a_scale[row] * b_scale[col] of the split operands
+int launch_gemm_tc(const __half *a_split, const float *a_scale, const __half *b_split, const float *b_scale, float *C,
+                   int64_t Mp, int NK, int Dp, cudaStream_t st);
 // logits GEMM with the classifier arg-max fused into the epilogue (K a multiple of 128); scratch: Mp * NK/128 * 8 bytes
 bool gemm_tc_argmax_supported(int NK, int K);
-int launch_gemm_tc_argmax(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, int64_t Mp, int NK, int Dp,
-                          const float *bias, int64_t B, int N, int K, void *scratch, int32_t *idx, cudaStream_t st);
+int launch_gemm_tc_argmax(const __half *a_split, const float *a_scale, const __half *b_split, const float *b_scale,
+                          int64_t Mp, int NK, int Dp, const float *bias, int64_t B, int N, int K, void *scratch,
+                          int32_t *idx, cudaStream_t st);
 int launch_argmax_init(const float *logits, const float *bias, int64_t B, int N, int K, int32_t *idx, cudaStream_t st);
 // work_counter (optional, device, zeroed by the caller on `st`): lets the warps of the search kernel fetch frames
 // dynamically instead of striding over the batch (frames take 2..iters passes, so static striding leaves a tail)

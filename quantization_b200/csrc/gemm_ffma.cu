@@ -1,5 +1,5 @@
 // gemm_ffma.cu -- plain fp32 CUDA-core GEMM  C (M, NK) = (a_scale * A) (M, D) . Bm (NK, D)^T.
-// Used as the cross-check of the tcgen05 bf16x3 GEMM (gemm_tc.cu) in the tests and for shapes the tensor-core
+// Used as the cross-check of the tcgen05 fp16x2 GEMM (gemm_tc.cu) in the tests and for shapes the tensor-core
 // kernel does not tile (dim not a multiple of 64); also holds the classifier arg-max (quantization.py:297-301).
 #include "common.cuh"
 

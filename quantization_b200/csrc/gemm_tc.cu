@@ -1,16 +1,18 @@
 // gemm_tc.cu -- fp32-faithful GEMM on the 5th-generation tensor cores:  C (Mp, NK) fp32 = A (Mp, D) . B (NK, D)^T
-// with both operands given as exact three-way bf16 splits a = a0 + a1 + a2 (8 significand bits each).
-// The six leading cross products  a0b0 + a0b1 + a1b0 + a0b2 + a1b1 + a2b0  are issued as tcgen05.mma kind::f16
-// (bf16 in, fp32 accumulate in TMEM); the dropped terms are below 2^-23 of |a||b| per element, i.e. under the
-// rounding noise of the fp32 accumulation itself.  A single-pass bf16 or tf32 GEMM flips 0.1-7 % of the codes
-// (SURVEY.md section 0 fact 3), which is why the split is there.
+// with both operands given as row-scaled two-way fp16 splits a 2^e = a0 + a1 (11 significand bits each, prepare.cu).
+// The three leading cross products  a0b0 + a0b1 + a1b0  are issued as tcgen05.mma kind::f16 (fp16 in, fp32 accumulate
+// in TMEM) -- products of fp16 pieces are exact in fp32; the dropped a1b1 term is <= 2^-22 |a b| per element, under the
+// rounding noise of the fp32 accumulation itself -- and the epilogue multiplies by the rows' exact 2^-e factors.
+// (Round 1 started with a three-way bf16 split and six products: same accuracy class, twice the MMA work.)
+// A single-pass bf16 or tf32 GEMM flips 0.1-7 % of the codes, which is why the split is
+// there.
 //
 // This replaces the reference's `to_logits(x)` addmm (quantization.py:279) and the per-pass scoring matmul
 // (quantization.py:413-416; here done once per frame as P = x Cs^T, see search.cu).
 //
-// Structure: persistent CTAs (one per SM), 128 x BN output tile, K blocks of 64 bf16 (one 128-byte swizzle atom).
-//   warp 0      TMA producer: per K block 3 A-plane boxes + 3 B-plane boxes -> 128B-swizzled smem, 2-stage ring
-//   warp 1      TMEM allocator + single-thread MMA issuer (24 tcgen05.mma per K block), tcgen05.commit -> mbarriers
+// Structure: persistent CTAs (one per SM), 128 x BN output tile, K blocks of 64 fp16 (one 128-byte swizzle atom).
+//   warp 0      TMA producer: per K block 2 A-plane boxes + 2 B-plane boxes -> 128B-swizzled smem, 3-stage ring
+//   warp 1      TMEM allocator + single-thread MMA issuer (12 tcgen05.mma per K block), tcgen05.commit -> mbarriers
 //   warps 2..5  epilogue: tcgen05.ld 32x32b.x32 -> registers -> 16-byte global stores, overlapped with the next
 //               tile's MMAs through a double-buffered TMEM accumulator
 #include <cuda.h>
@@ -22,24 +24,25 @@ namespace mcq {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 64;  // bf16 elements = 128 bytes = one swizzle atom row
-constexpr int STAGES = 2;
+constexpr int BK = 64;  // fp16 elements = 128 bytes = one swizzle atom row
+constexpr int STAGES = 3;
+constexpr int PLANES = 2;
 constexpr int NUM_THREADS = 192;
 
 template <int BN>
 struct TcCfg {
     static constexpr uint32_t A_PLANE = BM * 128;  // bytes of one plane of the A stage
     static constexpr uint32_t B_PLANE = BN * 128;
-    static constexpr uint32_t STAGE = 3 * A_PLANE + 3 * B_PLANE;
+    static constexpr uint32_t STAGE = PLANES * A_PLANE + PLANES * B_PLANE;
     static constexpr uint32_t SMEM = STAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
-    // Two fp32 accumulators per tile -- `main` takes only the a0*b0 products, `corr` the five small cross terms --
+    // Two fp32 accumulators per tile -- `main` takes only the a0*b0 products, `corr` the two small cross terms --
     // double buffered.  The tensor core truncates when it adds into the accumulator, so every MMA costs up to an
-    // ulp of |acc|; keeping the 5/6 of the MMAs that carry < 2^-8 of the magnitude out of the main accumulator
-    // cuts that bias six-fold (measured: 1.3e-6 -> see profiles/gemm_accuracy.md, relative to sum|x_d c_d|).
+    // ulp of |acc|; keeping the MMAs that carry < 2^-11 of the magnitude out of the main accumulator keeps that
+    // bias to one MMA per K step.
     static constexpr uint32_t TMEM_COLS = 4 * BN;
-    // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M   (cute::UMMA::InstrDescriptor bit layout)
-    static constexpr uint32_t IDESC =
-        (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // instruction descriptor: D=f32 (bit 4), A=B=f16 (format fields 0), both K-major, N, M
+    // (cute::UMMA::InstrDescriptor bit layout)
+    static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -82,7 +85,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -108,19 +111,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 
-// the six products kept (plane of A, plane of B): five corrections, smallest first, then the main product
-__device__ constexpr int kProdA[6] = {2, 1, 0, 1, 0, 0};
-__device__ constexpr int kProdB[6] = {0, 1, 2, 0, 1, 0};
+// the three products kept (plane of A, plane of B): the two corrections, then the main product
+constexpr int NPROD = 3;
+__device__ constexpr int kProdA[NPROD] = {1, 0, 0};
+__device__ constexpr int kProdB[NPROD] = {0, 1, 0};
 
 // ARGMAX: instead of storing the tile, the epilogue adds `bias` and keeps, per row, the first maximum of the tile's BN
 // columns: part_val / part_idx [row][n_tile] (the classifier arg-max of quantization.py:297-301 fused into the GEMM;
 // argmax_merge_kernel folds the K / BN tiles of a codebook).
 template <int BN, bool ARGMAX>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+gemm_fp16x2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                    float *__restrict__ C, int m_tiles, int n_tiles, int k_blocks, int ldc, int a_plane_rows,
-                   int b_plane_rows, const float *__restrict__ bias, float *__restrict__ part_val,
-                   int *__restrict__ part_idx) {
+                   int b_plane_rows, const float *__restrict__ a_scale, const float *__restrict__ b_scale,
+                   const float *__restrict__ bias, float *__restrict__ part_val, int *__restrict__ part_idx) {
     using Cfg = TcCfg<BN>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -173,10 +177,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     const uint32_t st = base + s * Cfg::STAGE;
                     mbar_expect_tx(full_bar(s), Cfg::STAGE);
 #pragma unroll
-                    for (int p = 0; p < 3; ++p) {
+                    for (int p = 0; p < PLANES; ++p) {
                         tma_load_2d(st + p * Cfg::A_PLANE, &tma_a, kb * BK, p * a_plane_rows + m0, full_bar(s));
-                        tma_load_2d(st + 3 * Cfg::A_PLANE + p * Cfg::B_PLANE, &tma_b, kb * BK, p * b_plane_rows + n0,
-                                    full_bar(s));
+                        tma_load_2d(st + PLANES * Cfg::A_PLANE + p * Cfg::B_PLANE, &tma_b, kb * BK,
+                                    p * b_plane_rows + n0, full_bar(s));
                     }
                     if (++s == STAGES) {
                         s = 0;
@@ -202,16 +206,16 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st = base + s * Cfg::STAGE;
 #pragma unroll
-                    for (int pr = 0; pr < 6; ++pr) {
+                    for (int pr = 0; pr < NPROD; ++pr) {
                         const uint32_t a_addr = st + kProdA[pr] * Cfg::A_PLANE;
-                        const uint32_t b_addr = st + 3 * Cfg::A_PLANE + kProdB[pr] * Cfg::B_PLANE;
+                        const uint32_t b_addr = st + PLANES * Cfg::A_PLANE + kProdB[pr] * Cfg::B_PLANE;
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
-                            if (pr == 5)
-                                umma_bf16(tmem_main, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32),
+                            if (pr == NPROD - 1)
+                                umma_f16(tmem_main, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32),
                                           Cfg::IDESC, (kb | k) != 0 ? 1u : 0u);
                             else
-                                umma_bf16(tmem_corr, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32),
+                                umma_f16(tmem_corr, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32),
                                           Cfg::IDESC, (kb | pr | k) != 0 ? 1u : 0u);
                         }
                     }
@@ -238,6 +242,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             mbar_wait(tfull_bar(acc), aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float *crow = C + (size_t)(m0 + q * 32 + lane) * ldc + n0;
+            const float sa = __ldg(a_scale + m0 + q * 32 + lane);  // 2^-e of my row of A
             float best = 0.0f;
             int bk = -1;
 #pragma unroll 1
@@ -247,11 +252,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 tmem_ld32(lane_base, r);
                 tmem_ld32(lane_base + (uint32_t)BN, rc);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const float *sbp = b_scale + n0 + c * 32;  // 2^-e of the rows of B = my columns
                 if constexpr (ARGMAX) {
                     const float *bs = bias + n0 + c * 32;
 #pragma unroll
                     for (int v = 0; v < 32; ++v) {
-                        const float val = (__uint_as_float(r[v]) + __uint_as_float(rc[v])) + __ldg(bs + v);
+                        const float val =
+                            (__uint_as_float(r[v]) + __uint_as_float(rc[v])) * (sa * __ldg(sbp + v)) + __ldg(bs + v);
                         if (bk < 0 || val > best) {  // first maximum wins, like torch.argmax
                             best = val;
                             bk = n0 + c * 32 + v;
@@ -260,11 +267,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 } else {
 #pragma unroll
                     for (int v = 0; v < 8; ++v) {
+                        const float4 sb = __ldg(reinterpret_cast<const float4 *>(sbp) + v);
                         float4 o;
-                        o.x = __uint_as_float(r[4 * v + 0]) + __uint_as_float(rc[4 * v + 0]);
-                        o.y = __uint_as_float(r[4 * v + 1]) + __uint_as_float(rc[4 * v + 1]);
-                        o.z = __uint_as_float(r[4 * v + 2]) + __uint_as_float(rc[4 * v + 2]);
-                        o.w = __uint_as_float(r[4 * v + 3]) + __uint_as_float(rc[4 * v + 3]);
+                        o.x = (__uint_as_float(r[4 * v + 0]) + __uint_as_float(rc[4 * v + 0])) * (sa * sb.x);
+                        o.y = (__uint_as_float(r[4 * v + 1]) + __uint_as_float(rc[4 * v + 1])) * (sa * sb.y);
+                        o.z = (__uint_as_float(r[4 * v + 2]) + __uint_as_float(rc[4 * v + 2])) * (sa * sb.z);
+                        o.w = (__uint_as_float(r[4 * v + 3]) + __uint_as_float(rc[4 * v + 3])) * (sa * sb.w);
                         *reinterpret_cast<float4 *>(crow + c * 32 + 4 * v) = o;
                     }
                 }
@@ -316,10 +324,10 @@ int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint
         return MCQ_ECUDA;
     }
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {cols * sizeof(__nv_bfloat16)};
+    cuuint64_t strides[1] = {cols * sizeof(__half)};
     cuuint32_t box[2] = {BK, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -331,15 +339,16 @@ int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint
 }
 
 template <int BN, bool ARGMAX>
-int launch_bn(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, float *C, int64_t Mp, int NK, int Dp,
-              cudaStream_t st, const float *bias = nullptr, float *part_val = nullptr, int *part_idx = nullptr) {
+int launch_bn(const __half *a_split, const float *a_scale, const __half *b_split, const float *b_scale, float *C,
+              int64_t Mp, int NK, int Dp, cudaStream_t st, const float *bias = nullptr, float *part_val = nullptr,
+              int *part_idx = nullptr) {
     using Cfg = TcCfg<BN>;
     const uint64_t NKp = align_up((size_t)NK, 128);
     CUtensorMap ma, mb;
     int rc;
-    if ((rc = make_map(&ma, a_split, 3ull * (uint64_t)Mp, (uint64_t)Dp, BM))) return rc;
-    if ((rc = make_map(&mb, b_split, 3ull * NKp, (uint64_t)Dp, BN))) return rc;
-    auto kern = gemm_bf16x3_kernel<BN, ARGMAX>;
+    if ((rc = make_map(&ma, a_split, (uint64_t)PLANES * (uint64_t)Mp, (uint64_t)Dp, BM))) return rc;
+    if ((rc = make_map(&mb, b_split, (uint64_t)PLANES * NKp, (uint64_t)Dp, BN))) return rc;
+    auto kern = gemm_fp16x2_kernel<BN, ARGMAX>;
     MCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     int dev = 0, sms = 148;
     MCQ_CUDA(cudaGetDevice(&dev));
@@ -347,23 +356,23 @@ int launch_bn(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, float 
     const int m_tiles = (int)(Mp / BM), n_tiles = NK / BN;
     int64_t tiles = (int64_t)m_tiles * n_tiles;
     int grid = (int)(tiles < sms ? tiles : sms);
-    kern<<<grid, NUM_THREADS, Cfg::SMEM, st>>>(ma, mb, C, m_tiles, n_tiles, Dp / BK, NK, (int)Mp, (int)NKp, bias, part_val,
-                                               part_idx);
-    MCQ_LAUNCH_CHECK("gemm_bf16x3_kernel");
+    kern<<<grid, NUM_THREADS, Cfg::SMEM, st>>>(ma, mb, C, m_tiles, n_tiles, Dp / BK, NK, (int)Mp, (int)NKp, a_scale, b_scale,
+                                               bias, part_val, part_idx);
+    MCQ_LAUNCH_CHECK("gemm_fp16x2_kernel");
     return MCQ_OK;
 }
 
 }  // namespace
 
-int launch_gemm_tc(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, float *C, int64_t Mp, int NK, int Dp,
-                   cudaStream_t st) {
+int launch_gemm_tc(const __half *a_split, const float *a_scale, const __half *b_split, const float *b_scale, float *C,
+                   int64_t Mp, int NK, int Dp, cudaStream_t st) {
     if (Mp <= 0) return MCQ_OK;
     if (Mp % BM != 0 || Dp % BK != 0 || NK % 64 != 0) {
         set_error("gemm_tc: Mp=%lld Dp=%d NK=%d not tile aligned", (long long)Mp, Dp, NK);
         return MCQ_EINVAL;
     }
-    if (NK % 128 == 0) return launch_bn<128, false>(a_split, b_split, C, Mp, NK, Dp, st);
-    return launch_bn<64, false>(a_split, b_split, C, Mp, NK, Dp, st);
+    if (NK % 128 == 0) return launch_bn<128, false>(a_split, a_scale, b_split, b_scale, C, Mp, NK, Dp, st);
+    return launch_bn<64, false>(a_split, a_scale, b_split, b_scale, C, Mp, NK, Dp, st);
 }
 
 // idx[b][n] = first maximum over the K / 128 tile maxima of codebook n (ascending tile = ascending column order)
@@ -391,8 +400,9 @@ bool gemm_tc_argmax_supported(int NK, int K) { return NK % 128 == 0 && K % 128 =
 
 // logits GEMM with the classifier arg-max fused into its epilogue: idx (B, N) int32.  `scratch` holds
 // Mp * (NK / 128) * 8 bytes of per-tile maxima.
-int launch_gemm_tc_argmax(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_split, int64_t Mp, int NK, int Dp,
-                          const float *bias, int64_t B, int N, int K, void *scratch, int32_t *idx, cudaStream_t st) {
+int launch_gemm_tc_argmax(const __half *a_split, const float *a_scale, const __half *b_split, const float *b_scale,
+                          int64_t Mp, int NK, int Dp, const float *bias, int64_t B, int N, int K, void *scratch,
+                          int32_t *idx, cudaStream_t st) {
     if (Mp <= 0) return MCQ_OK;
     if (Mp % BM != 0 || Dp % BK != 0 || !gemm_tc_argmax_supported(NK, K)) {
         set_error("gemm_tc_argmax: Mp=%lld Dp=%d NK=%d K=%d not supported", (long long)Mp, Dp, NK, K);
@@ -401,7 +411,7 @@ int launch_gemm_tc_argmax(const __nv_bfloat16 *a_split, const __nv_bfloat16 *b_s
     const int n_tiles = NK / 128;
     float *part_val = (float *)scratch;
     int *part_idx = (int *)(part_val + (size_t)Mp * n_tiles);
-    int rc = launch_bn<128, true>(a_split, b_split, nullptr, Mp, NK, Dp, st, bias, part_val, part_idx);
+    int rc = launch_bn<128, true>(a_split, a_scale, b_split, b_scale, nullptr, Mp, NK, Dp, st, bias, part_val, part_idx);
     if (rc) return rc;
     int64_t blocks = (B * N + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;

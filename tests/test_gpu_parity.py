@@ -164,7 +164,7 @@ def test_search_versions_agree(N, D, B, quantised):
 
 @pytest.mark.parametrize("name", golden_case_names())
 def test_xct_accuracy(golden_cases, name):
-    """P = x Cs^T from the tcgen05 bf16x3 GEMM (or the FFMA kernel for untiled shapes) against fp64."""
+    """P = x Cs^T from the tcgen05 fp16x2 GEMM (or the FFMA kernel for untiled shapes) against fp64."""
     g, meta = golden_cases
     m, x, p, q = _case(meta, name)
     xd = x.to(DEV)
