@@ -354,6 +354,61 @@ def test_round_trip_properties_full_size():
     assert torch.equal(idx7[fixed], idx6[fixed])
 
 
+@pytest.mark.parametrize("D,N,B,dt", [(768, 8, 262144, torch.float16),      # BASELINE config 5 at full size
+                                      (1024, 16, 131072, torch.float32),    # config 4: one GPU's slice of a chunk
+                                      (256, 4, 65536, torch.bfloat16)])     # config 3 (phase-2 shape) batch
+def test_full_size_properties_other_configs(D, N, B, dt):
+    """Size-independent properties at the sizes BASELINE.json names: (i) chunking / batch-composition invariance (a
+    4,096-frame window anywhere in the batch encodes to the same codes alone), (ii) half-precision frames encode like
+    their fp32 up-cast, (iii) five passes never reconstruct worse than the classifier arg-max alone, (iv) one more
+    pass leaves converged frames unchanged, (v) decode(uint8 codes) == decode(int64 indexes)."""
+    p = synth.synth_params(D, N, 256, 0)
+    q = make_quantizer(D, N, 256, p, DEV)
+    x = synth.synth_x(B, D, 1234 + N, dt).to(DEV)
+    codes = q.encode(x)
+    assert tuple(codes.shape) == (B, N) and codes.dtype == torch.uint8
+    lo = B // 2 - 1111
+    assert torch.equal(q.encode(x[lo:lo + 4096]), codes[lo:lo + 4096])
+    if dt != torch.float32:
+        assert torch.equal(q.encode(x[:8192].float()), codes[:8192])
+    with torch.no_grad():
+        xf = x.float()
+        dec = q.decode(codes)
+        e5 = ((dec - xf) ** 2).sum().item()
+        e0 = ((q.decode(q.encode(x, refine_indexes_iters=0)) - xf) ** 2).sum().item()
+        assert e5 < e0
+        assert torch.equal(q.decode(codes[:4096].to(torch.int64)), dec[:4096])
+    idx5 = codes[:16384].to(torch.int64)
+    idx6 = q._refine_indexes(x[:16384], idx5)
+    idx7 = q._refine_indexes(x[:16384], idx6)
+    fixed = (idx6 == idx5).all(1)
+    assert fixed.float().mean().item() > 0.5
+    assert torch.equal(idx7[fixed], idx6[fixed])
+
+
+def test_trainer_step_at_config3_batch():
+    """BASELINE config 3 batch (65,536 bf16 frames, dim 256, 4 bytes per frame): a few steps in each phase run, the
+    phase switch produces the (256, 4) quantizer, and the reconstruction loss goes down within each phase."""
+    import random
+    from quantization_b200 import QuantizerTrainer
+    torch.manual_seed(1)
+    random.seed(1)
+    tr = QuantizerTrainer(dim=256, bytes_per_frame=4, device=DEV, phase_one_iters=12, phase_two_iters=12)
+    x = synth.synth_x(65536, 256, 99, torch.bfloat16).to(DEV)
+    losses = {1: [], 2: []}
+    steps = 0
+    while not tr.done():
+        phase = 1 if tr.cur_iter <= tr.phase_one_iters else 2
+        with torch.no_grad():
+            losses[phase].append(float(tr.quantizer.compute_loss(x, 1)[0]))
+        tr.step(x)
+        steps += 1
+    assert steps == 25
+    qf = tr.get_quantizer()
+    assert (qf.codebook_size, qf.num_codebooks) == (256, 4)
+    assert losses[1][-1] < losses[1][0] and losses[2][-1] < losses[2][1]
+
+
 def test_edge_cases():
     from quantization_b200 import Quantizer
     q = Quantizer(64, 16, 4).to(DEV)
