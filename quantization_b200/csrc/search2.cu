@@ -25,6 +25,10 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int K2 = 256;
+#ifndef MCQ_POP_UNROLL
+#define MCQ_POP_UNROLL 4  // the pop loop is the bulk of the code; full unrolling costs instruction-cache misses
+#endif
+constexpr int POP_UNROLL = MCQ_POP_UNROLL;
 #ifndef MCQ_S2_WPC
 #define MCQ_S2_WPC 5
 #endif
@@ -105,7 +109,7 @@ __device__ __forceinline__ void select_sorted(Mem &s, const float (&key)[8], con
     // a lane reads back only its own column: no warp synchronisation needed here
     const float2 *col = &s.lists[0][lane];
     float2 head = col[0], nxt = col[32];  // the successor is fetched ahead so that a pop does not wait on shared memory
-#pragma unroll
+#pragma unroll(POP_UNROLL)
     for (int r = 0; r < R; ++r) {
         const float m = credux_min(head.x);
         // among the lanes holding the minimum the lowest flat index wins (contract: ascending (key, flat))
@@ -367,6 +371,7 @@ __device__ __forceinline__ void merge4_final(WarpMem2<N> &s, const float *__rest
     for (int i = 0; i < 32; ++i) dot[i] = 0.0f;
     // table T_ab: lane (hi, q) computes rows p = 8*hi + t of column q -- a request reads two G rows x 16 columns
     const int q = lane & 15, pb = (lane >> 4) * 8;
+    const int tbase = trow_off(pb) + q;
 #pragma unroll 1
     for (int lb = 0; lb < 4; ++lb) {
         const int b = 4 + lb;
@@ -398,7 +403,7 @@ __device__ __forceinline__ void merge4_final(WarpMem2<N> &s, const float *__rest
             const float v = s.uv[b][a][q];
             const float w = gat(G, s.rowoff[a] + cbo);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) s.tab[trow_off(pb + t) + q] = ((gv[t] - u[t]) - v) + w;
+            for (int t = 0; t < 8; ++t) s.tab[tbase + t * TSTR] = ((gv[t] - u[t]) - v) + w;  // = trow_off(pb + t) + q
             __syncwarp();
             const float4 *mine = reinterpret_cast<const float4 *>(&s.tab[trow_off((ti >> (4 * a)) & 15)]);
 #pragma unroll
@@ -621,6 +626,7 @@ __device__ __forceinline__ void wide_dots(WarpMem16 &s, const float *__restrict_
     for (int i = 0; i < 32; ++i) dot[i] = 0.0f;
     if constexpr (NA == 4) gather_uv_local<4, 4>(s, G, a_base, b_base, lane);  // all 16 pairs fit: c = la * 4 + lb
     const int q = lane & 15, pb = (lane >> 4) * 8;
+    const int tbase = trow_off(pb) + q;
 #pragma unroll 1
     for (int lb = 0; lb < NA; ++lb) {
         const int b = b_base + lb;
@@ -655,7 +661,7 @@ __device__ __forceinline__ void wide_dots(WarpMem16 &s, const float *__restrict_
             const float v = s.vl[c][q];
             const float w = gat(G, s.rowoff[a] + cbo);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) s.tab[trow_off(pb + t) + q] = ((gv[t] - u[t]) - v) + w;
+            for (int t = 0; t < 8; ++t) s.tab[tbase + t * TSTR] = ((gv[t] - u[t]) - v) + w;  // = trow_off(pb + t) + q
             __syncwarp();
             const float4 *mine = reinterpret_cast<const float4 *>(&s.tab[trow_off((ti >> (4 * la)) & 15)]);
 #pragma unroll
