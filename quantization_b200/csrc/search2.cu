@@ -693,35 +693,38 @@ __device__ __forceinline__ void merge4_16(WarpMem16 &s, const float *__restrict_
     float dot[32];
     wide_dots<4>(s, G, 8 * g, 8 * g + 4, ti, tj, lane, dot);
     const float kdo = s.kd3[o][lane];
-    // four selections over the row blocks i in [8r, 8r+8), then one over their 4 x 32 survivors
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int i = 0; i < 32; ++i) dot[i] = fmaf(2.0f, dot[i], s.kd3[e][i] + kdo);  // dot[] now holds the scores
+    // four selections over the row blocks i in [8r, 8r+8), then (r == 4) one over their 4 x 32 survivors.  One copy of
+    // the selection code: the loop is not unrolled, the block's scores are picked out of the register array by a switch.
+#pragma unroll 1
+    for (int r = 0; r < 5; ++r) {
         float key[8];
         int flat[8];
+        if (r < 4) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            key[t] = fmaf(2.0f, dot[8 * r + t], s.kd3[e][8 * r + t] + kdo);
-            flat[t] = (8 * r + t) * 32 + lane;
+            for (int t = 0; t < 8; ++t) {
+                key[t] = r == 0 ? dot[t] : (r == 1 ? dot[8 + t] : (r == 2 ? dot[16 + t] : dot[24 + t]));
+                flat[t] = (8 * r + t) * 32 + lane;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 c = s.cand[t][lane];  // block t holds flats in [256 t, 256 t + 256): ascending in t
+                key[t] = c.x;
+                flat[t] = __float_as_int(c.y);
+            }
+#pragma unroll
+            for (int t = 4; t < 8; ++t) {
+                key[t] = __int_as_float(0x7f800000);
+                flat[t] = 0x7ffffff0 + t;
+            }
         }
         select_sorted<WarpMem16, 32>(s, key, flat, lane);
-        s.cand[r][lane] = s.sel[lane];
-        __syncwarp();
-    }
-    {
-        float key[8];
-        int flat[8];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const float2 c = s.cand[t][lane];  // block t holds flats in [256 t, 256 t + 256): ascending in t
-            key[t] = c.x;
-            flat[t] = __float_as_int(c.y);
+        if (r < 4) {
+            s.cand[r][lane] = s.sel[lane];
+            __syncwarp();
         }
-#pragma unroll
-        for (int t = 4; t < 8; ++t) {
-            key[t] = __int_as_float(0x7f800000);
-            flat[t] = 0x7ffffff0 + t;
-        }
-        select_sorted<WarpMem16, 32>(s, key, flat, lane);
     }
     {
         const float2 r = s.sel[lane];
