@@ -381,36 +381,48 @@ __device__ __forceinline__ void merge4_final(WarpMem2<N> &s, const float *__rest
         float E[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) E[c] = 0.0f;
+        // the tables of two codebooks a are gathered together (16 loads in flight per lane) and folded in a order;
+        // the second table lives in the lists / es union, which is idle until E_b is written below
+        float *const tabs[2] = {&s.tab[0], &s.es[0][0]};
 #pragma unroll 1
-        for (int a = 0; a < 4; ++a) {
-            const unsigned msk = colu ? (s.used[a] >> pb) & 0xffu : 0u;  // rows of my half that are still in use
-            unsigned ra[8];
-            float u[8];
-            {
+        for (int ap = 0; ap < 4; ap += 2) {
+            float gv[2][8], w[2];
+#pragma unroll
+            for (int aa = 0; aa < 2; ++aa) {
+                const int a = ap + aa;
+                const unsigned msk = colu ? (s.used[a] >> pb) & 0xffu : 0u;  // rows of my half that are still in use
                 const uint4 *rp = reinterpret_cast<const uint4 *>(&s.rowk[a][pb]);
-                const float4 *up = reinterpret_cast<const float4 *>(&s.uv[a][b][pb]);
                 const uint4 r0 = rp[0], r1 = rp[1];
+                const unsigned ra[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    gv[aa][t] = 0.0f;
+                    if ((msk >> t) & 1u) gv[aa][t] = gat(G, ra[t] + cq);
+                }
+                w[aa] = gat(G, s.rowoff[a] + cbo);
+            }
+#pragma unroll
+            for (int aa = 0; aa < 2; ++aa) {
+                const int a = ap + aa;
+                const float4 *up = reinterpret_cast<const float4 *>(&s.uv[a][b][pb]);
                 const float4 u0 = up[0], u1 = up[1];
-                ra[0] = r0.x; ra[1] = r0.y; ra[2] = r0.z; ra[3] = r0.w; ra[4] = r1.x; ra[5] = r1.y; ra[6] = r1.z; ra[7] = r1.w;
-                u[0] = u0.x; u[1] = u0.y; u[2] = u0.z; u[3] = u0.w; u[4] = u1.x; u[5] = u1.y; u[6] = u1.z; u[7] = u1.w;
-            }
-            float gv[8];
+                const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                const float v = s.uv[b][a][q];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                gv[t] = 0.0f;
-                if ((msk >> t) & 1u) gv[t] = gat(G, ra[t] + cq);
+                for (int t = 0; t < 8; ++t)
+                    tabs[aa][tbase + t * TSTR] = ((gv[aa][t] - u[t]) - v) + w[aa];  // tbase + t*TSTR = trow_off(pb+t) + q
             }
-            const float v = s.uv[b][a][q];
-            const float w = gat(G, s.rowoff[a] + cbo);
-#pragma unroll
-            for (int t = 0; t < 8; ++t) s.tab[tbase + t * TSTR] = ((gv[t] - u[t]) - v) + w;  // = trow_off(pb + t) + q
             __syncwarp();
-            const float4 *mine = reinterpret_cast<const float4 *>(&s.tab[trow_off((ti >> (4 * a)) & 15)]);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float4 r = mine[c];
-                fadd2(E[4 * c + 0], E[4 * c + 1], r.x, r.y);
-                fadd2(E[4 * c + 2], E[4 * c + 3], r.z, r.w);
+            for (int aa = 0; aa < 2; ++aa) {
+                const float4 *mine =
+                    reinterpret_cast<const float4 *>(&tabs[aa][trow_off((ti >> (4 * (ap + aa))) & 15)]);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 r = mine[c];
+                    fadd2(E[4 * c + 0], E[4 * c + 1], r.x, r.y);
+                    fadd2(E[4 * c + 2], E[4 * c + 3], r.z, r.w);
+                }
             }
             __syncwarp();
         }
