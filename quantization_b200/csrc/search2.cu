@@ -125,6 +125,57 @@ __device__ __forceinline__ void select_sorted(Mem &s, const float (&key)[8], con
     __syncwarp();
 }
 
+// Two independent selections at once (same flat numbering): the two pop chains are interleaved, so the latency of one
+// chain's warp reductions is covered by the other's.  The second selection uses caller-supplied memory: `lists2` (10 rows
+// of 32 float2; row 8 gets the +inf sentinels here, row 9 is only ever prefetched) and `sel2` (R entries).
+template <class Mem, int R>
+__device__ __forceinline__ void select_sorted2(Mem &s, const float (&keyA)[8], const float (&keyB)[8],
+                                               const int (&flat)[8], int lane, float2 (*lists2)[32], float2 *sel2) {
+    int rankA[8], rankB[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) rankA[t] = rankB[t] = 7 - t;
+#pragma unroll
+    for (int t = 1; t < 8; ++t)
+#pragma unroll
+        for (int u = 0; u < t; ++u) {
+            const int ca = le_mask(keyA[u], keyA[t]), cb = le_mask(keyB[u], keyB[t]);
+            rankA[t] -= ca;
+            rankA[u] += ca;
+            rankB[t] -= cb;
+            rankB[u] += cb;
+        }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        s.lists[rankA[t]][lane] = make_float2(keyA[t], __int_as_float(flat[t]));
+        lists2[rankB[t]][lane] = make_float2(keyB[t], __int_as_float(flat[t]));
+    }
+    lists2[8][lane] = make_float2(__int_as_float(0x7f800000), __int_as_float(0));
+    const float2 *colA = &s.lists[0][lane], *colB = &lists2[0][lane];
+    float2 headA = colA[0], nxtA = colA[32], headB = colB[0], nxtB = colB[32];
+#pragma unroll(POP_UNROLL)
+    for (int r = 0; r < R; ++r) {
+        const float mA = credux_min(headA.x);
+        const float mB = credux_min(headB.x);
+        const unsigned fA = (headA.x == mA) ? (unsigned)__float_as_int(headA.y) : 0x7fffffffu;
+        const unsigned fB = (headB.x == mB) ? (unsigned)__float_as_int(headB.y) : 0x7fffffffu;
+        const unsigned wA = __reduce_min_sync(FULL, fA);
+        const unsigned wB = __reduce_min_sync(FULL, fB);
+        if (fA == wA && fA != 0x7fffffffu) {
+            s.sel[r] = headA;
+            headA = nxtA;
+            colA += 32;
+            nxtA = colA[32];
+        }
+        if (fB == wB && fB != 0x7fffffffu) {
+            sel2[r] = headB;
+            headB = nxtB;
+            colB += 32;
+            nxtB = colB[32];
+        }
+    }
+    __syncwarp();
+}
+
 // Flat index of the smallest of the warp's 256 candidates (lowest flat index among equals).
 __device__ __forceinline__ int select_best(const float (&key)[8], const int (&flat)[8], int lane) {
     float best = key[0];
@@ -141,61 +192,92 @@ __device__ __forceinline__ int select_best(const float (&key)[8], const int (&fl
     return w == 0x7fffffffu ? 0 : (int)w;  // the guard is only reachable with NaN scores
 }
 
-// Level 1 (quantization.py:401-418 with the per-codebook constants dropped) + top-16 per codebook.
+// Level-1 deltas of codebook n (quantization.py:401-418 with the per-codebook constants dropped):
+//   key[k] = v[k] - v[old_n],  v[k] = fmaf(2, sum_{m != n} G[(m,old_m),(n,k)] - P[n,k], G[(n,k),(n,k)])
 // Lane L owns entries 4L..4L+3 and 128+4L..128+4L+3, so every float4 request of the warp is 512 contiguous bytes.
 template <int N, class Mem>
-__device__ __forceinline__ void level1(Mem &s, const float *__restrict__ Pb, const float *__restrict__ Gp, int lane) {
+__device__ __forceinline__ void level1_keys(Mem &s, const float *__restrict__ Pb, const float *__restrict__ Gp, int n,
+                                            int lane, float (&key)[8]) {
     constexpr unsigned NK = N * K2;
     const float *diag = Gp + (size_t)NK * NK;
+    float acc[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = 0.0f;
+    const unsigned colbase = n * K2 + lane * 4;
+#pragma unroll(N <= 8 ? N - 1 : 5)  // rows in flight per batch: all N-1 up to 8 codebooks, 5 of the 15 at N = 16
+    for (int mm = 0; mm < N - 1; ++mm) {
+        const int m = mm + (mm >= n ? 1 : 0);  // ascending m, skipping n
+        const float4 *row = reinterpret_cast<const float4 *>(Gp + (s.rowoff[m] + colbase));
+        const float4 a = __ldg(row), b = __ldg(row + 32);
+        fadd2(acc[0], acc[1], a.x, a.y);
+        fadd2(acc[2], acc[3], a.z, a.w);
+        fadd2(acc[4], acc[5], b.x, b.y);
+        fadd2(acc[6], acc[7], b.z, b.w);
+    }
+    const float4 *pp = reinterpret_cast<const float4 *>(Pb + colbase);
+    const float4 *dp = reinterpret_cast<const float4 *>(diag + colbase);
+    const float4 p0 = __ldg(pp), p1 = __ldg(pp + 32), d0 = __ldg(dp), d1 = __ldg(dp + 32);
+    float v[8];
+    v[0] = fmaf(2.0f, acc[0] - p0.x, d0.x);
+    v[1] = fmaf(2.0f, acc[1] - p0.y, d0.y);
+    v[2] = fmaf(2.0f, acc[2] - p0.z, d0.z);
+    v[3] = fmaf(2.0f, acc[3] - p0.w, d0.w);
+    v[4] = fmaf(2.0f, acc[4] - p1.x, d1.x);
+    v[5] = fmaf(2.0f, acc[5] - p1.y, d1.y);
+    v[6] = fmaf(2.0f, acc[6] - p1.z, d1.z);
+    v[7] = fmaf(2.0f, acc[7] - p1.w, d1.w);
+    // v of the current entry old[n]: it lives in lane (old >> 2) & 31 as element (old & 3) + 4 * (old >= 128)
+    const int on = s.old[n];
+    const int tsel = (on & 3) | ((on >> 5) & 4);
+    float vs = v[0];
+#pragma unroll
+    for (int t = 1; t < 8; ++t) vs = (tsel == t) ? v[t] : vs;
+    const float vold = __shfl_sync(FULL, vs, (on >> 2) & 31);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) key[t] = v[t] - vold;
+}
+
+template <int N, class Mem>
+__device__ __forceinline__ void level1_store(Mem &s, int n, int lane, const float2 *sel) {
+    constexpr unsigned NK = N * K2;
+    if (lane < 16) {
+        const float2 r = sel[lane];
+        s.kd1[n][lane] = r.x;
+        s.kk[n][lane] = __float_as_int(r.y);  // flat index == codebook entry k
+        s.rowk[n][lane] = (unsigned)(n * K2 + __float_as_int(r.y)) * NK;
+    }
+}
+
+// Level 1 + top-16 per codebook.  PAIR: two codebooks per step with interleaved pop chains; the second selection's
+// lists live in the (not yet gathered) uv region and its result in the (not yet written) kd2 region.
+template <int N, class Mem, bool PAIR>
+__device__ __forceinline__ void level1(Mem &s, const float *__restrict__ Pb, const float *__restrict__ Gp, int lane) {
     int flat[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) flat[t] = (t < 4 ? 0 : 128 - 4) + lane * 4 + t;
+    if constexpr (PAIR) {
+        static_assert(sizeof(s.uv) >= 10 * 32 * sizeof(float2) && sizeof(s.kd2) >= 16 * sizeof(float2), "pair memory");
+        float2(*lists2)[32] = reinterpret_cast<float2(*)[32]>(&s.uv[0][0][0]);
+        float2 *sel2 = reinterpret_cast<float2 *>(&s.kd2[0][0]);
 #pragma unroll 1
-    for (int n = 0; n < N; ++n) {
-        float acc[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) acc[t] = 0.0f;
-        const unsigned colbase = n * K2 + lane * 4;
-#pragma unroll(N <= 8 ? N - 1 : 5)  // rows in flight per batch: all N-1 up to 8 codebooks, 5 of the 15 at N = 16
-        for (int mm = 0; mm < N - 1; ++mm) {
-            const int m = mm + (mm >= n ? 1 : 0);  // ascending m, skipping n
-            const float4 *row = reinterpret_cast<const float4 *>(Gp + (s.rowoff[m] + colbase));
-            const float4 a = __ldg(row), b = __ldg(row + 32);
-            fadd2(acc[0], acc[1], a.x, a.y);
-            fadd2(acc[2], acc[3], a.z, a.w);
-            fadd2(acc[4], acc[5], b.x, b.y);
-            fadd2(acc[6], acc[7], b.z, b.w);
+        for (int n = 0; n < N; n += 2) {
+            float keyA[8], keyB[8];
+            level1_keys<N, Mem>(s, Pb, Gp, n, lane, keyA);
+            level1_keys<N, Mem>(s, Pb, Gp, n + 1, lane, keyB);
+            select_sorted2<Mem, 16>(s, keyA, keyB, flat, lane, lists2, sel2);
+            level1_store<N, Mem>(s, n, lane, s.sel);
+            level1_store<N, Mem>(s, n + 1, lane, sel2);
+            __syncwarp();
         }
-        const float4 *pp = reinterpret_cast<const float4 *>(Pb + colbase);
-        const float4 *dp = reinterpret_cast<const float4 *>(diag + colbase);
-        const float4 p0 = __ldg(pp), p1 = __ldg(pp + 32), d0 = __ldg(dp), d1 = __ldg(dp + 32);
-        float v[8];
-        v[0] = fmaf(2.0f, acc[0] - p0.x, d0.x);
-        v[1] = fmaf(2.0f, acc[1] - p0.y, d0.y);
-        v[2] = fmaf(2.0f, acc[2] - p0.z, d0.z);
-        v[3] = fmaf(2.0f, acc[3] - p0.w, d0.w);
-        v[4] = fmaf(2.0f, acc[4] - p1.x, d1.x);
-        v[5] = fmaf(2.0f, acc[5] - p1.y, d1.y);
-        v[6] = fmaf(2.0f, acc[6] - p1.z, d1.z);
-        v[7] = fmaf(2.0f, acc[7] - p1.w, d1.w);
-        // v of the current entry old[n]: it lives in lane (old >> 2) & 31 as element (old & 3) + 4 * (old >= 128)
-        const int on = s.old[n];
-        const int tsel = (on & 3) | ((on >> 5) & 4);
-        float vs = v[0];
-#pragma unroll
-        for (int t = 1; t < 8; ++t) vs = (tsel == t) ? v[t] : vs;
-        const float vold = __shfl_sync(FULL, vs, (on >> 2) & 31);
-        float key[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) key[t] = v[t] - vold;
-        select_sorted<Mem, 16>(s, key, flat, lane);
-        if (lane < 16) {
-            const float2 r = s.sel[lane];
-            s.kd1[n][lane] = r.x;
-            s.kk[n][lane] = __float_as_int(r.y);  // flat index == codebook entry k
-            s.rowk[n][lane] = (unsigned)(n * K2 + __float_as_int(r.y)) * NK;
+    } else {
+#pragma unroll 1
+        for (int n = 0; n < N; ++n) {
+            float key[8];
+            level1_keys<N, Mem>(s, Pb, Gp, n, lane, key);
+            select_sorted<Mem, 16>(s, key, flat, lane);
+            level1_store<N, Mem>(s, n, lane, s.sel);
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
@@ -463,7 +545,7 @@ template <int N>
 __device__ __forceinline__ void refine_pass2(WarpMem2<N> &s, const float *__restrict__ Pb, const float *__restrict__ G, int lane) {
     if (lane < N) s.rowoff[lane] = (unsigned)(lane * K2 + s.old[lane]) * (unsigned)(N * K2);
     __syncwarp();
-    level1<N, WarpMem2<N>>(s, Pb, G, lane);
+    level1<N, WarpMem2<N>, (N == 8)>(s, Pb, G, lane);
     gather_uv<N>(s, G, lane);
     if constexpr (N == 2) {
         merge1<N, true>(s, G, 0, lane);
@@ -778,7 +860,7 @@ __device__ __forceinline__ void merge8_final_16(WarpMem16 &s, const float *__res
 __device__ __forceinline__ void refine_pass16(WarpMem16 &s, const float *__restrict__ Pb, const float *__restrict__ G, int lane) {
     if (lane < 16) s.rowoff[lane] = (unsigned)(lane * K2 + s.old[lane]) * (unsigned)(16 * K2);
     __syncwarp();
-    level1<16, WarpMem16>(s, Pb, G, lane);
+    level1<16, WarpMem16, false>(s, Pb, G, lane);
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) merge1_16(s, G, g, lane);
 #pragma unroll 1
