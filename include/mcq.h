@@ -106,16 +106,19 @@ int mcq_decode_backward(const float *grad_out, const int64_t *idx, int64_t num_f
  * the backward pass);  *logprob_sum = sum_{b,n} log_softmax(xw + bias)[b, n, idx[b,n]]  (:221-225 before the mean);
  * prob_sum (N*K) = sum_b softmax(xw + bias)[b, n, k]  (:235 before the mean).  idx (B, N) int64.
  * Backward: grad_logits (B, N*K) = d loss / d logits given g_logprob_sum (1 element) and g_prob_sum (N*K), both
- * DEVICE pointers (no host synchronisation).  The weight / bias / scale gradients are GEMMs of grad_logits the
- * host layer forms (as the reference's autograd does).
+ * DEVICE pointers (no host synchronisation).  part_gx (mcq_class_loss_partials() floats) receives partial sums of
+ * grad_logits * xw: their total times scale_speed is d loss / d logits_scale (logits = exp(ls*speed) x W^T + b, so
+ * no second GEMM is needed for it).  The weight / bias gradients are products of grad_logits the host layer forms
+ * (as the reference's autograd does).
  */
 int mcq_class_loss_forward(const void *x, int x_dtype, int64_t num_frames, int dim, int num_codebooks,
                            int codebook_size, const void *prepared, const int64_t *idx, float *xw,
                            float *logprob_sum, float *prob_sum, void *workspace, size_t workspace_bytes,
                            void *stream);
+int mcq_class_loss_partials(void);
 int mcq_class_loss_backward(const float *xw, int64_t num_frames, int dim, int num_codebooks, int codebook_size,
                             const void *prepared, const int64_t *idx, const float *g_logprob_sum,
-                            const float *g_prob_sum, float *grad_logits, void *stream);
+                            const float *g_prob_sum, float *grad_logits, float *part_gx, void *stream);
 
 /* Pointers into the prepared blob (device): scaled centers (N*K, D) fp32 and the Gram table (N*K, N*K). */
 const float *mcq_prepared_scaled_centers(const void *prepared, int num_codebooks, int codebook_size, int dim);

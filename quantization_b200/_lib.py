@@ -48,7 +48,8 @@ def lib():
         "mcq_decode_centers": (i32, [vp, i32, i64, i32, i32, i32, i32, vp, vp, i32, vp]),
         "mcq_decode_backward": (i32, [vp, vp, i64, i32, i32, i32, vp, vp]),
         "mcq_class_loss_forward": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
-        "mcq_class_loss_backward": (i32, [vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+        "mcq_class_loss_partials": (i32, []),
+        "mcq_class_loss_backward": (i32, [vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
         "mcq_prepared_scaled_centers": (vp, [vp, i32, i32, i32]),
         "mcq_prepared_gram": (vp, [vp, i32, i32, i32]),
         "mcq_xct": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, vp, sz, vp]),
@@ -67,7 +68,7 @@ def lib():
 
 EXPORTS = ["mcq_version", "mcq_last_error", "mcq_packed_cols", "mcq_prepared_bytes", "mcq_workspace_bytes",
            "mcq_prepare", "mcq_encode", "mcq_refine", "mcq_decode", "mcq_decode_centers", "mcq_decode_backward",
-           "mcq_class_loss_forward", "mcq_class_loss_backward",
+           "mcq_class_loss_forward", "mcq_class_loss_backward", "mcq_class_loss_partials",
            "mcq_prepared_scaled_centers", "mcq_prepared_gram", "mcq_xct", "mcq_search", "mcq_encode_host",
            "mcq_profile", "mcq_profile_read"]
 

@@ -468,22 +468,25 @@ int mcq_class_loss_forward(const void *x, int x_dtype, int64_t B, int D, int N, 
                                       logprob_sum, st));
 }
 
+int mcq_class_loss_partials(void) { return class_loss_bwd_partials(); }
+
 int mcq_class_loss_backward(const float *xw, int64_t B, int D, int N, int K, const void *prepared, const int64_t *idx,
-                            const float *g_logprob_sum, const float *g_prob_sum, float *grad_logits, void *stream) {
+                            const float *g_logprob_sum, const float *g_prob_sum, float *grad_logits, float *part_gx,
+                            void *stream) {
     int rc = check_shape(N, K, D);
     if (rc) return rc;
     if (B <= 0) {
         set_error("mcq_class_loss_backward: bad argument");
         return MCQ_EINVAL;
     }
-    if (!xw || !prepared || !idx || !g_logprob_sum || !g_prob_sum || !grad_logits) {
+    if (!xw || !prepared || !idx || !g_logprob_sum || !g_prob_sum || !grad_logits || !part_gx) {
         set_error("mcq_class_loss_backward: null pointer");
         return MCQ_EINVAL;
     }
     const Prepared L = prepared_layout(N, K, D);
     return PROF(MCQ_PROF_OTHER, (cudaStream_t)stream,
                 launch_class_loss_bwd(xw, (const float *)((const char *)prepared + L.off_bias), idx, B, N, K,
-                                      g_logprob_sum, g_prob_sum, grad_logits, (cudaStream_t)stream));
+                                      g_logprob_sum, g_prob_sum, grad_logits, part_gx, (cudaStream_t)stream));
 }
 
 int mcq_xct(const void *x, int x_dtype, int64_t B, int D, int N, int K, const void *prepared, float *P, void *workspace,

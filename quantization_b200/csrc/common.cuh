@@ -103,8 +103,9 @@ int launch_decode_backward(const float *grad_out, const int64_t *idx, int64_t B,
 int class_loss_streams(int64_t B, int N);
 int launch_class_loss_fwd(const float *xw, const float *bias, const int64_t *idx, int64_t B, int N, int K,
                           float *part_prob, float *part_lp, float *prob_sum, float *logprob_sum, cudaStream_t st);
+int class_loss_bwd_partials();
 int launch_class_loss_bwd(const float *xw, const float *bias, const int64_t *idx, int64_t B, int N, int K,
-                          const float *g_lp, const float *g_prob, float *grad_logits, cudaStream_t st);
+                          const float *g_lp, const float *g_prob, float *grad_logits, float *part_gx, cudaStream_t st);
 
 bool use_tensor_core_gemm();
 

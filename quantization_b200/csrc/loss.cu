@@ -35,13 +35,17 @@ __device__ __forceinline__ float seg_sum(float v) {
 // K < 16 = W with EPL = 1 and the upper lanes idle).  Returns softmax s[] and log-softmax ls[] of (xw + bias).
 template <int W, int EPL>
 __device__ __forceinline__ void row_softmax(const float *__restrict__ xw, const float *__restrict__ bias, int K,
-                                            int sl, float (&s)[EPL], float (&ls)[EPL]) {
+                                            int sl, float (&s)[EPL], float (&ls)[EPL], float (&raw)[EPL]) {
     float l[EPL];
     if constexpr (EPL >= 4) {
 #pragma unroll
         for (int t = 0; t < EPL; t += 4) {
             const float4 a = *reinterpret_cast<const float4 *>(xw + sl * EPL + t);
             const float4 c = __ldg(reinterpret_cast<const float4 *>(bias + sl * EPL + t));
+            raw[t] = a.x;
+            raw[t + 1] = a.y;
+            raw[t + 2] = a.z;
+            raw[t + 3] = a.w;
             l[t] = a.x + c.x;
             l[t + 1] = a.y + c.y;
             l[t + 2] = a.z + c.z;
@@ -51,7 +55,8 @@ __device__ __forceinline__ void row_softmax(const float *__restrict__ xw, const 
 #pragma unroll
         for (int t = 0; t < EPL; ++t) {
             const int k = sl * EPL + t;
-            l[t] = k < K ? xw[k] + __ldg(bias + k) : -INFINITY;
+            raw[t] = k < K ? xw[k] : 0.0f;
+            l[t] = k < K ? raw[t] + __ldg(bias + k) : -INFINITY;
         }
     }
     float m = l[0];
@@ -94,8 +99,8 @@ __global__ void __launch_bounds__(256) class_loss_fwd_kernel(const float *__rest
         const int64_t b = b0 + st;
         const bool on = live && b < B;
         const int64_t br = on ? b : 0;
-        float s[EPL], ls[EPL];
-        row_softmax<W, EPL>(xw + (size_t)br * NK + (size_t)n * K, bias + (size_t)n * K, K, sl, s, ls);
+        float s[EPL], ls[EPL], raw[EPL];
+        row_softmax<W, EPL>(xw + (size_t)br * NK + (size_t)n * K, bias + (size_t)n * K, K, sl, s, ls, raw);
         const int kc = (int)idx[(size_t)br * N + n];
         if (on) {
 #pragma unroll
@@ -152,21 +157,23 @@ __global__ void __launch_bounds__(256) class_loss_bwd_kernel(const float *__rest
                                                              const int64_t *__restrict__ idx, int64_t B, int N, int K,
                                                              const float *__restrict__ g_lp,
                                                              const float *__restrict__ g_prob,
-                                                             float *__restrict__ grad_logits) {
+                                                             float *__restrict__ grad_logits,
+                                                             float *__restrict__ part_gx) {
     constexpr int SPW = 32 / W;
     const int lane = threadIdx.x & 31, sl = lane % W;
     const int64_t rows = B * N;
     const size_t NK = (size_t)N * K;
     const float glp = *g_lp;
     const int64_t nseg = (int64_t)gridDim.x * (blockDim.x >> 5) * SPW;
+    float gx = 0.0f;  // sum of grad_logits * xw over this lane's elements: d loss / d logits_scale up to a factor
     for (int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * SPW; r0 < rows; r0 += nseg) {
         const int64_t r = r0 + lane / W;
         const bool on = r < rows;
         const int64_t rr = on ? r : 0;
         const int64_t b = rr / N;
         const int n = (int)(rr - b * N);
-        float s[EPL], ls[EPL];
-        row_softmax<W, EPL>(xw + (size_t)b * NK + (size_t)n * K, bias + (size_t)n * K, K, sl, s, ls);
+        float s[EPL], ls[EPL], raw[EPL];
+        row_softmax<W, EPL>(xw + (size_t)b * NK + (size_t)n * K, bias + (size_t)n * K, K, sl, s, ls, raw);
         const int kc = (int)idx[rr];
         float c[EPL];
         float dotc = 0.0f;
@@ -182,6 +189,8 @@ __global__ void __launch_bounds__(256) class_loss_bwd_kernel(const float *__rest
 #pragma unroll
         for (int t = 0; t < EPL; ++t) o[t] = glp * ((sl * EPL + t == kc ? 1.0f : 0.0f) - s[t]) + s[t] * (c[t] - dotc);
         if (on) {
+#pragma unroll
+            for (int t = 0; t < EPL; ++t) gx += o[t] * raw[t];  // (raw is 0 on the idle lanes of K < 16)
             if constexpr (EPL >= 4) {
 #pragma unroll
                 for (int t = 0; t < EPL; t += 4)
@@ -193,6 +202,9 @@ __global__ void __launch_bounds__(256) class_loss_bwd_kernel(const float *__rest
             }
         }
     }
+    // fixed work assignment + shuffle tree: the per-warp partials (and their sum in warp order) are reproducible
+    gx = seg_sum<32>(gx);
+    if (lane == 0) part_gx[blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = gx;
 }
 
 // K -> (segment width, elements per lane)
@@ -236,8 +248,11 @@ int launch_class_loss_fwd(const float *xw, const float *bias, const int64_t *idx
     return MCQ_OK;
 }
 
+int class_loss_bwd_partials() { return 148 * 8 * 8; }
+
 int launch_class_loss_bwd(const float *xw, const float *bias, const int64_t *idx, int64_t B, int N, int K,
-                          const float *g_lp, const float *g_prob, float *grad_logits, cudaStream_t st) {
+                          const float *g_lp, const float *g_prob, float *grad_logits, float *part_gx,
+                          cudaStream_t st) {
     if (K > 256) {
         set_error("class loss: codebook_size %d > 256", K);
         return MCQ_EUNSUPPORTED;
@@ -245,8 +260,10 @@ int launch_class_loss_bwd(const float *xw, const float *bias, const int64_t *idx
     const int spw = K >= 32 ? 1 : 2;
     int64_t blocks = (B * N + 8 * spw - 1) / (8 * spw);
     if (blocks > 148 * 8) blocks = 148 * 8;
-#define MCQ_BWD(W, EPL) \
-    class_loss_bwd_kernel<W, EPL><<<(unsigned)blocks, 256, 0, st>>>(xw, bias, idx, B, N, K, g_lp, g_prob, grad_logits)
+    MCQ_CUDA(cudaMemsetAsync(part_gx, 0, sizeof(float) * class_loss_bwd_partials(), st));  // unused warps stay 0
+#define MCQ_BWD(W, EPL)                                                                                              \
+    class_loss_bwd_kernel<W, EPL><<<(unsigned)blocks, 256, 0, st>>>(xw, bias, idx, B, N, K, g_lp, g_prob, grad_logits, \
+                                                                    part_gx)
     MCQ_LOSS_DISPATCH(K, MCQ_BWD)
 #undef MCQ_BWD
     MCQ_LAUNCH_CHECK("class_loss_bwd_kernel");

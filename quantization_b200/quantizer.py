@@ -92,17 +92,20 @@ class _ClassLossFn(torch.autograd.Function):
         g_lp = g_lp.reshape(1).float().contiguous()
         g_prob = g_prob.reshape(N * K).float().contiguous()
         grad_logits = torch.empty(B, N * K, dtype=torch.float32, device=x.device)
+        part_gx = torch.empty(L.mcq_class_loss_partials(), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             rc = L.mcq_class_loss_backward(xw.data_ptr(), B, D, N, K, ctx.blob.data_ptr(), indexes.data_ptr(),
                                            g_lp.data_ptr(), g_prob.data_ptr(), grad_logits.data_ptr(),
-                                           _lib.stream_ptr(x.device))
+                                           part_gx.data_ptr(), _lib.stream_ptr(x.device))
         _lib.check(rc, "mcq_class_loss_backward")
         scale = (logits_scale.detach() * q.scale_speed).exp()
         xs = scale * x.float()                       # what the reference feeds to_logits (quantization.py:278)
         grad_w = grad_logits.t().mm(xs)              # (N*K, D)
         grad_b = grad_logits.sum(dim=0)
-        grad_xs = grad_logits.mm(weight.detach())    # (B, D)
-        grad_ls = (grad_xs * xs).sum() * q.scale_speed
+        # d/d logits_scale: logits = xs W^T + b with d xs / d logits_scale = speed * xs, so the gradient is
+        # speed * sum(grad_logits * (xs W^T)); xs W^T is the saved forward product and the kernel above already
+        # summed the products: no second GEMM, no extra pass
+        grad_ls = part_gx.sum() * q.scale_speed
         return None, None, None, grad_w, grad_b, grad_ls.reshape(logits_scale.shape)
 
 
