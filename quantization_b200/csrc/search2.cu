@@ -29,8 +29,27 @@ constexpr int K2 = 256;
 #define MCQ_POP_UNROLL 4  // the pop loop is the bulk of the code; full unrolling costs instruction-cache misses
 #endif
 constexpr int POP_UNROLL = MCQ_POP_UNROLL;
+// Launch shape: ONE CTA of 16 warps per SM (128 registers per thread).  Measured at C2 (75,776 frames, static striding):
+// 4 CTAs x 5 warps (96 regs) 5.59 ms, 2 x 8 (128 regs) 5.12 ms, 1 x 20 (96 regs) 5.40 ms, 1 x 12 (152 regs) 5.23 ms,
+// 1 x 16 (128 regs) 4.90 ms: fewer, fatter warps win (no spills, and the shared memory one CTA does not take stays L1).
+// N = 2, 4: one CTA of 24 warps (0.92 vs 0.97 ms for 3 x 8 at N = 4); N = 16: two CTAs of 8 warps (10.9 vs 11.2 ms for 4 x 4).
+#ifndef MCQ_S2_MINB
+#define MCQ_S2_MINB 1
+#endif
 #ifndef MCQ_S2_WPC
-#define MCQ_S2_WPC 5
+#define MCQ_S2_WPC 16
+#endif
+#ifndef MCQ_S2_WPC4
+#define MCQ_S2_WPC4 24
+#endif
+#ifndef MCQ_S2_MINB4
+#define MCQ_S2_MINB4 1
+#endif
+#ifndef MCQ_S16_WPC
+#define MCQ_S16_WPC 8
+#endif
+#ifndef MCQ_S16_MINB
+#define MCQ_S16_MINB 2
 #endif
 
 __device__ __forceinline__ float credux_min(float v) {
@@ -870,9 +889,9 @@ __device__ __forceinline__ void refine_pass16(WarpMem16 &s, const float *__restr
     merge8_final_16(s, G, lane);
 }
 
-constexpr int WPC16 = 4;
+constexpr int WPC16 = MCQ_S16_WPC;
 
-__global__ void __launch_bounds__(WPC16 * 32, 4)
+__global__ void __launch_bounds__(WPC16 * 32, MCQ_S16_MINB)
     search2_kernel16(const float *__restrict__ P, const float *__restrict__ G, int64_t B, int iters, const int32_t *__restrict__ idx_in,
                      int32_t *__restrict__ idx_out, unsigned *__restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -929,11 +948,12 @@ int launch16(const float *P, const float *Gp, int64_t B, int iters, const int32_
 
 template <int N>
 struct Launch2 {
-    static constexpr int WPC = (N == 8) ? MCQ_S2_WPC : 8;  // warps per CTA
+    static constexpr int WPC = (N == 8) ? MCQ_S2_WPC : MCQ_S2_WPC4;  // warps per CTA
+    static constexpr int MINB = (N == 8) ? MCQ_S2_MINB : MCQ_S2_MINB4;
 };
 
 template <int N>
-__global__ void __launch_bounds__(Launch2<N>::WPC * 32, (N == 8 ? 4 : 3))
+__global__ void __launch_bounds__(Launch2<N>::WPC * 32, Launch2<N>::MINB)
     search2_kernel(const float *__restrict__ P, const float *__restrict__ G, int64_t B, int iters, const int32_t *__restrict__ idx_in,
                    int32_t *__restrict__ idx_out, unsigned *__restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
