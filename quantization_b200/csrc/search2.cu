@@ -361,6 +361,7 @@ __device__ __forceinline__ void merge1(WarpMem2<N> &s, const float *__restrict__
     }
     if constexpr (FINAL) {
         const int fl = select_best(key, flat, lane);
+        __syncwarp();  // every lane has read old[] (above) before lane 0 overwrites it
         if (lane == 0) {
             const int ne = s.kk[e][fl >> 4], no = s.kk[o][fl & 15];
             s.old[e] = ne;
@@ -430,6 +431,7 @@ __device__ __forceinline__ void merge2(WarpMem2<N> &s, const float *__restrict__
     }
     if constexpr (FINAL) {
         const int fl = select_best(key, flat, lane);
+        __syncwarp();  // every lane has read old[] (above) before lane 0 overwrites it
         if (lane == 0) {
             const unsigned te = s.kt2[e][fl >> 4], to = s.kt2[o][fl & 15];
             const int n0 = s.kk[a0][te & 15], n1 = s.kk[a1][te >> 4];
