@@ -34,7 +34,9 @@ struct TcCfg {
     static constexpr uint32_t A_PLANE = BM * 128;  // bytes of one plane of the A stage
     static constexpr uint32_t B_PLANE = BN * 128;
     static constexpr uint32_t STAGE = PLANES * A_PLANE + PLANES * B_PLANE;
-    static constexpr uint32_t SMEM = STAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    // epilogue staging: per epilogue warp 32 rows x (32 + 4) floats, so that the global stores are full 128-byte rows
+    static constexpr uint32_t EPI_STAGE = 4 * 32 * 36 * 4;
+    static constexpr uint32_t SMEM = STAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_STAGE;
     // Two fp32 accumulators per tile -- `main` takes only the a0*b0 products, `corr` the two small cross terms --
     // double buffered.  The tensor core truncates when it adds into the accumulator, so every MMA costs up to an
     // ulp of |acc|; keeping the MMAs that carry < 2^-11 of the magnitude out of the main accumulator keeps that
@@ -265,6 +267,9 @@ gemm_fp16x2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                         }
                     }
                 } else {
+                    // scale, transpose through shared memory, store full rows: lane l writes 16 bytes of row
+                    // (l / 8 + 4 k), so one instruction covers four complete 128-byte row segments
+                    float *stg = reinterpret_cast<float *>(smem_raw + (bar_base + 256u - smem_u32(smem_raw))) + q * (32 * 36);
 #pragma unroll
                     for (int v = 0; v < 8; ++v) {
                         const float4 sb = __ldg(reinterpret_cast<const float4 *>(sbp) + v);
@@ -273,8 +278,17 @@ gemm_fp16x2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                         o.y = (__uint_as_float(r[4 * v + 1]) + __uint_as_float(rc[4 * v + 1])) * (sa * sb.y);
                         o.z = (__uint_as_float(r[4 * v + 2]) + __uint_as_float(rc[4 * v + 2])) * (sa * sb.z);
                         o.w = (__uint_as_float(r[4 * v + 3]) + __uint_as_float(rc[4 * v + 3])) * (sa * sb.w);
-                        *reinterpret_cast<float4 *>(crow + c * 32 + 4 * v) = o;
+                        *reinterpret_cast<float4 *>(stg + lane * 36 + 4 * v) = o;
                     }
+                    __syncwarp();
+                    float *cbase = C + (size_t)(m0 + q * 32) * ldc + n0 + c * 32 + (lane & 7) * 4;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int row = k * 4 + (lane >> 3);
+                        const float4 o = *reinterpret_cast<const float4 *>(stg + row * 36 + (lane & 7) * 4);
+                        *reinterpret_cast<float4 *>(cbase + (size_t)row * ldc) = o;
+                    }
+                    __syncwarp();
                 }
             }
             if constexpr (ARGMAX) {
