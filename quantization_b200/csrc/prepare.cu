@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) split_x_kernel(const T *__restrict__ x, i
                                                       const float *__restrict__ scal, float *__restrict__ xf,
                                                       __half *__restrict__ xsplit, __half *__restrict__ lsplit,
                                                       float *__restrict__ xscale, float *__restrict__ lscale,
-                                                      bool want_logits) {
+                                                      bool want_logits, bool want_xf) {
     const float ls = scal[1];
     const size_t plane = (size_t)Mp * Dp;
     const int lane = threadIdx.x & 31;
@@ -194,10 +194,10 @@ __global__ void __launch_bounds__(256) split_x_kernel(const T *__restrict__ x, i
         if (live)
             for (int d = lane; d < D; d += 32) {
                 const float v = to_f32<T>(x[(size_t)r * D + d]);
-                xf[(size_t)r * D + d] = v;
+                if (want_xf) xf[(size_t)r * D + d] = v;
                 mx = fmaxf(mx, fabsf(v));
             }
-        else
+        else if (want_xf)
             for (int d = lane; d < D; d += 32) xf[(size_t)r * D + d] = 0.f;
         mx = warp_max_f(mx);
         float sx, ix, sl = 1.f, il = 1.f;
@@ -233,18 +233,20 @@ int launch_split_x(const void *x, int x_dtype, int64_t B, const Prepared &L, con
     float *xf = (float *)(ws + W.off_xf);
     __half *xs = (__half *)(ws + W.off_xsplit), *lsp = (__half *)(ws + W.off_lsplit);
     float *xsc = (float *)(ws + W.off_xscale), *lsc = (float *)(ws + W.off_lscale);
+    // the fp32 copy is only read by the CUDA-core GEMM (shapes the tcgen05 kernel does not tile, MCQ_GEMM=ffma)
+    const bool want_xf = !(use_tensor_core_gemm() && L.NK % 64 == 0);
     switch (x_dtype) {
         case MCQ_F32:
             split_x_kernel<float><<<blocks, 256, 0, st>>>((const float *)x, B, W.Mp, L.D, L.Dp, scal, xf, xs, lsp, xsc,
-                                                          lsc, want_logits_split);
+                                                          lsc, want_logits_split, want_xf);
             break;
         case MCQ_F16:
             split_x_kernel<__half><<<blocks, 256, 0, st>>>((const __half *)x, B, W.Mp, L.D, L.Dp, scal, xf, xs, lsp, xsc,
-                                                           lsc, want_logits_split);
+                                                           lsc, want_logits_split, want_xf);
             break;
         case MCQ_BF16:
             split_x_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16 *)x, B, W.Mp, L.D, L.Dp, scal,
-                                                                  xf, xs, lsp, xsc, lsc, want_logits_split);
+                                                                  xf, xs, lsp, xsc, lsc, want_logits_split, want_xf);
             break;
         default:
             set_error("unknown x dtype %d", x_dtype);
