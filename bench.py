@@ -312,7 +312,8 @@ def run_ours(args, rank, world, local_rank):
                 "frames_per_launch": frames_per_launch, "avg_launch_ms": search_avg_ms,
                 "share_of_step": s_ms / args.steps / ms,
                 "note": "algorithmic flops are the reference formulation's (SURVEY 8d); the kernel replaces them by "
-                        "Gram-table lookups, so it is L2-gather/issue bound, not tensor bound (DESIGN.md)"}
+                        "Gram-table lookups, so its own bound is the L1 data pipe (3.9 k wavefronts per frame-pass = "
+                        "4.0 ms per 75,776-frame launch at 100 %; ncu: 77 % busy), not the tensor pipe (DESIGN.md 3)"}
     gemm_flop_exec = 3 * 2.0 * DIM * NCB * KSZ * frames_per_launch  # three fp16 products per GEMM launch
     extra = {
         "gemm": {"kernel": "gemm_fp16x2_kernel<128> (tcgen05, 3 MMAs per K step; the logits GEMM carries the fused arg-max epilogue)", "launches": g_n, "avg_launch_ms": g_ms / max(g_n, 1),
