@@ -92,6 +92,10 @@ bool search2_supports(int N, int K);
 int launch_search2(const float *P, const float *gram, int64_t B, int N, int K, int iters, const int32_t *idx_in,
                    int32_t *idx_out, cudaStream_t st, unsigned *work_counter);
 int64_t max_chunk_frames();
+// codebook_size 16, 8 codebooks (trainer phase 1 at bytes_per_frame = 4): Gram table in shared memory, sub-warp selections
+bool search_k16_supports(int N, int K);
+int launch_search_k16(const float *P, const float *gram, int64_t B, int iters, const int32_t *idx_in, int32_t *idx_out,
+                      cudaStream_t st, unsigned *work_counter);
 int launch_pack(const int32_t *idx, int64_t B, int N, int K, void *codes, int codes_dtype, cudaStream_t st);
 int launch_i64_to_i32(const int64_t *src, int32_t *dst, int64_t n, int K, cudaStream_t st);
 int launch_i32_to_i64(const int32_t *src, int64_t *dst, int64_t n, cudaStream_t st);

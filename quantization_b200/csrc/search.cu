@@ -393,6 +393,7 @@ int launch_search(const float *P, const float *gram, int64_t B, int N, int K, in
         const char *e = getenv("MCQ_SEARCH");
         const bool force_v1 = e && strcmp(e, "v1") == 0;
         if (!force_v1 && search2_supports(N, K)) return launch_search2(P, gram, B, N, K, iters, idx_in, idx_out, st, work_counter);
+        if (!force_v1 && search_k16_supports(N, K)) return launch_search_k16(P, gram, B, iters, idx_in, idx_out, st, work_counter);
     }
     switch (K) {
         case 2: return dispatch_n<2>(N, P, gram, B, iters, idx_in, idx_out, st);

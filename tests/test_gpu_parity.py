@@ -162,6 +162,37 @@ def test_search_versions_agree(N, D, B, quantised):
         del os.environ["MCQ_SEARCH"]
 
 
+@pytest.mark.parametrize("quantised", [False, True])
+def test_search_k16_kernel_agrees(quantised):
+    """codebook_size 16 x 8 codebooks (trainer phase 1): the shared-memory kernel (search_k16.cu) against the generic
+    first-version kernel and the bit-level CPU model, also with coarsely quantised tables (many exact ties)."""
+    K, N, D, B = 16, 8, 256, 30000
+    p = synth.synth_params(D, N, K, 21)
+    if quantised:
+        p = {k: (v * 4).round() / 4 for k, v in p.items()}
+    q = make_quantizer(D, N, K, p, DEV)
+    x = synth.synth_x(B, D, 4322)
+    if quantised:
+        x = (x * 2).round() / 2
+    xd = x.to(DEV)
+    P = _xct(q, xd)
+    _, gr = _prepared_views(q)
+    NK = N * K
+    for idx0 in (synth.synth_indexes(B, N, K, 6).numpy(),
+                 q.encode(xd, refine_indexes_iters=0, as_bytes=False).cpu().numpy()):
+        outs = {}
+        for ver in ("v1", "v2"):
+            os.environ["MCQ_SEARCH"] = ver
+            try:
+                outs[ver] = _search(P, gr, idx0, N, K, 3)
+            finally:
+                del os.environ["MCQ_SEARCH"]
+        nbad = int((outs["v1"] != outs["v2"]).any(1).sum())
+        assert nbad == 0, f"{nbad}/{B} frames differ between the two search kernels"
+        ref = gm.search(P.cpu().numpy(), gr[:NK * NK].reshape(NK, NK).cpu().numpy(), idx0, N, K, 3)
+        assert np.array_equal(outs["v2"], ref)
+
+
 @pytest.mark.parametrize("name", golden_case_names())
 def test_xct_accuracy(golden_cases, name):
     """P = x Cs^T from the tcgen05 fp16x2 GEMM (or the FFMA kernel for untiled shapes) against fp64."""

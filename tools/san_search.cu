@@ -11,7 +11,8 @@
 #include "../include/mcq.h"
 
 int main(int argc, char **argv) {
-    const int N = argc > 1 ? atoi(argv[1]) : 8, B = argc > 2 ? atoi(argv[2]) : 256, K = 256, iters = 3;
+    const int N = argc > 1 ? atoi(argv[1]) : 8, B = argc > 2 ? atoi(argv[2]) : 256, iters = 3;
+    const int K = argc > 4 ? atoi(argv[4]) : 256;
     const int mode = argc > 3 ? atoi(argv[3]) : 0;  // 1: heavily quantised values (many exactly equal scores), 2: all zero
     const size_t NK = (size_t)N * K;
     std::vector<float> G(NK * NK + NK), P((size_t)B * NK);
