@@ -54,6 +54,9 @@ struct Cfg {
     static constexpr int LIST = N * CUT1;             // entries of the level-1 lists (the largest)
     static constexpr int LIST2 = HALF * CUT1;         // entries of any later list
     static constexpr int TABN = CUT1 * CUT1;
+    // K >= 32 with N >= 32 reaches cutoff 64 (quantization.py:455-463): one or two merges of 64 x 64 joint candidates,
+    // too many to keep in registers -- they are accumulated in shared memory (Level::run_big)
+    static constexpr int BIGN = (BASE == 16 && N >= 32) ? 4096 : 1;
 };
 
 // Per-warp shared memory.
@@ -66,6 +69,7 @@ struct WarpSmem {
     float kd[2][C::LIST];                    // kept deltas (ping-pong between levels)
     unsigned kt[2][C::LIST2 > 0 ? C::LIST2 : 1][C::TW];  // kept slot tuples of levels >= 2
     float tab[C::HALF][C::TABN];             // D_ab tables of the codebook pairs being merged
+    unsigned big[C::BIGN];                   // dots, then sortable keys, of a 4096-candidate merge
 };
 
 // Removes and returns the smallest (key, candidate) of the warp's CPL*32 candidates, candidate c = t*32 + lane.
@@ -105,12 +109,151 @@ struct Level {
     static constexpr int CUT1 = C::CUT1;
     static constexpr int TPL = (CUT1 * CUT1) / 32;  // table entries per lane
 
-    __device__ static __forceinline__ void run(WarpSmem<K, N> &s, const float *__restrict__ G, int cur, int lane) {
-        static_assert(Kc * Kc >= 32 && Kc <= 32, "joint candidate count per merge must be 64..1024");
-        const int nxt = cur ^ 1;
+    // The L tables D_ab = ((g - u) - v) + w of codebook b against every codebook a of the even group (only the slots
+    // the kept candidates still use).
+    __device__ static __forceinline__ void build_tables(WarpSmem<K, N> &s, const float *__restrict__ G, int e, int b,
+                                                        int lane) {
         const size_t NK = C::NK;
+        const size_t cb_old = (size_t)b * K + s.old[b];
+        const unsigned umb = s.um[b];
 #pragma unroll 1
-        for (int m = 0; m < NEWN; ++m) {
+        for (int la = 0; la < L; ++la) {
+            const int a = e * L + la;
+            const size_t ra_old = ((size_t)a * K + s.old[a]) * NK;
+            const unsigned uma = s.um[a];
+            const float w = __ldg(G + ra_old + cb_old);
+#pragma unroll
+            for (int tt = 0; tt < (TPL > 0 ? TPL : 1); ++tt) {
+                const int ent = tt * 32 + lane;
+                const int q = ent % CUT1, p = ent / CUT1;
+                if (ent < CUT1 * CUT1 && ((uma >> p) & 1u) && ((umb >> q) & 1u)) {
+                    const size_t ra = ((size_t)a * K + s.kk[a][p]) * NK;
+                    const size_t cb = (size_t)b * K + s.kk[b][q];
+                    const float g = __ldg(G + ra + cb);
+                    const float u = __ldg(G + ra + cb_old);
+                    const float v = __ldg(G + ra_old + cb);
+                    s.tab[la][ent] = ((g - u) - v) + w;
+                }
+            }
+        }
+    }
+
+    // Stores the r-th kept candidate (flat index c = i*Kc + j) of merged group m, or the final indexes.
+    __device__ static __forceinline__ void emit(WarpSmem<K, N> &s, int cur, int m, int r, unsigned mk, int c) {
+        const int nxt = cur ^ 1;
+        const int e = 2 * m, o = 2 * m + 1;
+        const int ci = c / Kc, cj = c % Kc;
+        unsigned te[C::TW], to[C::TW];
+        if constexpr (L == 1) {
+            te[0] = (unsigned)ci;
+            to[0] = (unsigned)cj;
+        } else {
+#pragma unroll
+            for (int w = 0; w < C::TW; ++w) {
+                te[w] = s.kt[cur][e * Kc + ci][w];
+                to[w] = s.kt[cur][o * Kc + cj][w];
+            }
+        }
+        if constexpr (NEWN == 1) {
+            // final winner: tuple covers all N codebooks; decode slots to codebook entries
+#pragma unroll 1
+            for (int la = 0; la < L; ++la) {
+                s.old[la] = s.kk[la][nib<C::TW>(te, la)];
+                s.old[L + la] = s.kk[L + la][nib<C::TW>(to, la)];
+            }
+        } else {
+            unsigned tn[C::TW];
+#pragma unroll
+            for (int w = 0; w < C::TW; ++w) tn[w] = 0u;
+            if constexpr (L < 8) {
+                tn[0] = te[0] | (to[0] << (4 * L));
+            } else {
+#pragma unroll
+                for (int w = 0; w < L / 8; ++w) {
+                    tn[w] = te[w];
+                    tn[L / 8 + w] = to[w];
+                }
+            }
+            s.kd[nxt][m * NEWK + r] = fkey_inv(mk);
+#pragma unroll
+            for (int w = 0; w < C::TW; ++w) s.kt[nxt][m * NEWK + r][w] = tn[w];
+        }
+    }
+
+    // Merge of group pair m with Kc = 64: the 4096 dots / keys live in shared memory, candidate c = i*64 + j is owned by
+    // lane c % 32 (so j = lane or lane + 32).  Same arithmetic and tie rules as the register path below.
+    __device__ static __forceinline__ void merge_big(WarpSmem<K, N> &s, const float *__restrict__ G, int cur, int m,
+                                                     int lane) {
+        constexpr int NC = Kc * Kc, PER = NC / 32;
+        const int e = 2 * m, o = 2 * m + 1;
+        unsigned tj[2][C::TW];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int w = 0; w < C::TW; ++w) tj[h][w] = s.kt[cur][o * Kc + h * 32 + lane][w];
+#pragma unroll 4
+        for (int t = 0; t < PER; ++t) s.big[t * 32 + lane] = __float_as_uint(0.0f);
+#pragma unroll 1
+        for (int lb = 0; lb < L; ++lb) {
+            const int b = o * L + lb;
+            const int sj0 = nib<C::TW>(tj[0], lb), sj1 = nib<C::TW>(tj[1], lb);
+            build_tables(s, G, e, b, lane);
+            __syncwarp();
+#pragma unroll 2
+            for (int t = 0; t < PER; ++t) {
+                const int i = t >> 1;
+                const int sjb = (t & 1) ? sj1 : sj0;
+                unsigned ti[C::TW];
+#pragma unroll
+                for (int w = 0; w < C::TW; ++w) ti[w] = s.kt[cur][e * Kc + i][w];
+                float w = 0.0f;
+#pragma unroll
+                for (int la = 0; la < L; ++la) w = w + s.tab[la][nib<C::TW>(ti, la) * CUT1 + sjb];
+                s.big[t * 32 + lane] = __float_as_uint(__uint_as_float(s.big[t * 32 + lane]) + w);
+            }
+            __syncwarp();
+        }
+        // keys; each lane keeps the smallest (key, t) of its own 128
+        const float dj0 = s.kd[cur][o * Kc + lane], dj1 = s.kd[cur][o * Kc + 32 + lane];
+        unsigned lk = KEY_REMOVED;
+        int lt = 0;
+#pragma unroll 2
+        for (int t = 0; t < PER; ++t) {
+            const float base = s.kd[cur][e * Kc + (t >> 1)] + ((t & 1) ? dj1 : dj0);
+            const unsigned k = fkey(fmaf(2.0f, __uint_as_float(s.big[t * 32 + lane]), base));
+            s.big[t * 32 + lane] = k;
+            if (k < lk) {
+                lk = k;
+                lt = t;
+            }
+        }
+#pragma unroll 1
+        for (int r = 0; r < NEWK; ++r) {
+            const unsigned mk = __reduce_min_sync(FULL, lk);
+            const unsigned c = (lk == mk) ? (unsigned)(lt * 32 + lane) : 0xffffffffu;
+            const unsigned cw = __reduce_min_sync(FULL, c);
+            if (lane == 0) emit(s, cur, m, r, mk, (int)cw);
+            if (NEWK > 1 && c == cw) {  // the owner removes it and rescans its column
+                s.big[cw] = KEY_REMOVED;
+                lk = KEY_REMOVED;
+                lt = 0;
+#pragma unroll 4
+                for (int t = 0; t < PER; ++t) {
+                    const unsigned k = s.big[t * 32 + lane];
+                    if (k < lk) {
+                        lk = k;
+                        lt = t;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // Merge of group pair m with at most 1024 joint candidates: dots and keys in registers.
+    __device__ static __forceinline__ void merge_regs(WarpSmem<K, N> &s, const float *__restrict__ G, int cur, int m,
+                                                      int lane) {
+        {
             const int e = 2 * m, o = 2 * m + 1;
             // this lane's fixed right-hand candidate j and its slot tuple
             const int j = lane % Kc;
@@ -129,29 +272,7 @@ struct Level {
             for (int lb = 0; lb < L; ++lb) {
                 const int b = o * L + lb;
                 const int sjb = nib<C::TW>(tj, lb);
-                const size_t cb_old = (size_t)b * K + s.old[b];
-                const unsigned umb = s.um[b];
-                // ---- build the L tables D_ab, a in the even group (only the slots still in use) ----
-#pragma unroll 1
-                for (int la = 0; la < L; ++la) {
-                    const int a = e * L + la;
-                    const size_t ra_old = ((size_t)a * K + s.old[a]) * NK;
-                    const unsigned uma = s.um[a];
-                    const float w = __ldg(G + ra_old + cb_old);
-#pragma unroll
-                    for (int tt = 0; tt < (TPL > 0 ? TPL : 1); ++tt) {
-                        const int ent = tt * 32 + lane;
-                        const int q = ent % CUT1, p = ent / CUT1;
-                        if (ent < CUT1 * CUT1 && ((uma >> p) & 1u) && ((umb >> q) & 1u)) {
-                            const size_t ra = ((size_t)a * K + s.kk[a][p]) * NK;
-                            const size_t cb = (size_t)b * K + s.kk[b][q];
-                            const float g = __ldg(G + ra + cb);
-                            const float u = __ldg(G + ra + cb_old);
-                            const float v = __ldg(G + ra_old + cb);
-                            s.tab[la][ent] = ((g - u) - v) + w;
-                        }
-                    }
-                }
+                build_tables(s, G, e, b, lane);
                 __syncwarp();
                 // ---- accumulate: dot(i,j) += sum_a D_ab[slot_i(a)][slot_j(b)] ----
 #pragma unroll
@@ -187,57 +308,38 @@ struct Level {
                 int c;
                 extract_min<CPL>(key, lane, mk, c);
                 // candidate c = t*32 + lane  ->  flat = i*Kc + j with i = c / Kc, j = c % Kc: identical numbering
-                if (lane == 0) {
-                    const int ci = c / Kc, cj = c % Kc;
-                    unsigned te[C::TW], to[C::TW];
-                    if constexpr (L == 1) {
-                        te[0] = (unsigned)ci;
-                        to[0] = (unsigned)cj;
-                    } else {
-#pragma unroll
-                        for (int w = 0; w < C::TW; ++w) {
-                            te[w] = s.kt[cur][e * Kc + ci][w];
-                            to[w] = s.kt[cur][o * Kc + cj][w];
-                        }
-                    }
-                    if constexpr (NEWN == 1) {
-                        // final winner: tuple covers all N codebooks; decode slots to codebook entries
-#pragma unroll
-                        for (int la = 0; la < L; ++la) {
-                            s.old[la] = s.kk[la][nib<C::TW>(te, la)];
-                            s.old[L + la] = s.kk[L + la][nib<C::TW>(to, la)];
-                        }
-                    } else {
-                        unsigned tn[C::TW];
-#pragma unroll
-                        for (int w = 0; w < C::TW; ++w) tn[w] = 0u;
-                        if constexpr (L < 8) {
-                            tn[0] = te[0] | (to[0] << (4 * L));
-                        } else {
-#pragma unroll
-                            for (int w = 0; w < L / 8; ++w) {
-                                tn[w] = te[w];
-                                tn[L / 8 + w] = to[w];
-                            }
-                        }
-                        s.kd[nxt][m * NEWK + r] = fkey_inv(mk);
-#pragma unroll
-                        for (int w = 0; w < C::TW; ++w) s.kt[nxt][m * NEWK + r][w] = tn[w];
-                    }
-                }
+                if (lane == 0) emit(s, cur, m, r, mk, c);
             }
             __syncwarp();
+        }
+    }
+
+    __device__ static __forceinline__ void run(WarpSmem<K, N> &s, const float *__restrict__ G, int cur, int lane) {
+        static_assert(Kc * Kc >= 32 && Kc <= 64, "joint candidate count per merge must be 64..4096");
+        const int nxt = cur ^ 1;
+#pragma unroll 1
+        for (int m = 0; m < NEWN; ++m) {
+            if constexpr (Kc == 64)
+                merge_big(s, G, cur, m, lane);
+            else
+                merge_regs(s, G, cur, m, lane);
         }
         if constexpr (NEWN > 1) {
             // used-slot masks of the new lists
 #pragma unroll 1
             for (int m = 0; m < NEWN; ++m) {
-                unsigned t[C::TW];
+                unsigned t[(NEWK + 31) / 32][C::TW];
 #pragma unroll
-                for (int w = 0; w < C::TW; ++w) t[w] = (lane < NEWK) ? s.kt[nxt][m * NEWK + lane][w] : 0u;
+                for (int h = 0; h < (NEWK + 31) / 32; ++h)
 #pragma unroll
+                    for (int w = 0; w < C::TW; ++w)
+                        t[h][w] = (h * 32 + lane < NEWK) ? s.kt[nxt][m * NEWK + h * 32 + lane][w] : 0u;
+#pragma unroll 1
                 for (int la = 0; la < 2 * L; ++la) {
-                    unsigned bit = (lane < NEWK) ? (1u << nib<C::TW>(t, la)) : 0u;
+                    unsigned bit = 0u;
+#pragma unroll
+                    for (int h = 0; h < (NEWK + 31) / 32; ++h)
+                        if (h * 32 + lane < NEWK) bit |= 1u << nib<C::TW>(t[h], la);
                     bit = __reduce_or_sync(FULL, bit);
                     if (lane == 0) s.um[m * 2 * L + la] = (unsigned short)bit;
                 }
@@ -375,8 +477,8 @@ int dispatch_n(int N, const float *P, const float *G, int64_t B, int iters, cons
         case 4: if constexpr (K >= 16) return launch_one<K, 4>(P, G, B, iters, idx_in, idx_out, st); break;
         case 8: if constexpr (K >= 16) return launch_one<K, 8>(P, G, B, iters, idx_in, idx_out, st); break;
         case 16: if constexpr (K >= 16) return launch_one<K, 16>(P, G, B, iters, idx_in, idx_out, st); break;
-        case 32: if constexpr (K == 16) return launch_one<K, 32>(P, G, B, iters, idx_in, idx_out, st); break;
-        case 64: if constexpr (K == 16) return launch_one<K, 64>(P, G, B, iters, idx_in, idx_out, st); break;
+        case 32: if constexpr (K >= 16) return launch_one<K, 32>(P, G, B, iters, idx_in, idx_out, st); break;
+        case 64: if constexpr (K >= 16) return launch_one<K, 64>(P, G, B, iters, idx_in, idx_out, st); break;
         default: break;
     }
     set_error("search: (K=%d, N=%d) is not supported by this build", K, N);

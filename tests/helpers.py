@@ -50,5 +50,6 @@ def make_quantizer(D, N, K, params, device, centers_scale=0.0, logits_scale=0.0)
 
 
 def search_supported(N, K):
-    """(K, N) pairs the CUDA search kernel is built for (4096-candidate merges are not)."""
-    return not (N >= 32 and K > 16)
+    """(K, N) pairs the CUDA search kernels are built for: everything the reference itself supports up to
+    codebook_size 256 and 64 codebooks (K < 16 with N > 1 crashes in the reference, quantization.py:453,470,504-507)."""
+    return K <= 256 and N <= 64 and (N == 1 or K >= 16)
