@@ -120,6 +120,34 @@ int mcq_class_loss_backward(const float *xw, int64_t num_frames, int dim, int nu
                             const void *prepared, const int64_t *idx, const float *g_logprob_sum,
                             const float *g_prob_sum, float *grad_logits, float *part_gx, void *stream);
 
+/*
+ * JointCodebookLoss (reference prediction.py:9-82, class :86-197): the stages between its dense products.
+ * Layouts: hidden / grad_hidden (B, H) fp32 = linear1(predictor); codes (B, N) uint8 / int32 / int64 as produced by
+ * mcq_encode (negative = padding where the type allows it); embedding ((N-1)*K, H) fp32 = codebook_embedding.weight;
+ * act / grad_act (N, B, H) fp32: act[n, b, :] = relu(hidden[b] + sum_{m<n} scale * embedding[m*K + max(codes[b,m],0)])
+ * (prediction.py:47-68: embedding gather, concat, cumsum over codebooks, ReLU -- in the reference's summation order),
+ * stored codebook-major because it is the left operand of the per-codebook product with linear2_weight[n] (:70-72).
+ *   mcq_jcl_hidden_forward    writes act.
+ *   mcq_jcl_hidden_backward   given grad_act = d loss / d act: grad_hidden (overwritten) and grad_embedding
+ *                             (ACCUMULATED into with atomics: zero it first).
+ *   mcq_jcl_cross_entropy     logits (B, N, K) fp32 WITHOUT linear2_bias, bias (N, K): per-row cross entropy of
+ *                             softmax(logits + bias) against codes (:79-82) -> row_loss (B, N), 0 where codes ==
+ *                             ignore_index; sums[0] = total loss, sums[1] = number of rows counted (for reduction =
+ *                             'mean').  With want_grad != 0 the logits are overwritten by d sums[0] / d logits
+ *                             (softmax - onehot; 0 on ignored rows).  partials: mcq_jcl_partials() floats of scratch;
+ *                             the sums are formed in a fixed order (bitwise reproducible).
+ */
+int mcq_jcl_hidden_forward(const float *hidden, const void *codes, int codes_dtype, int64_t num_frames,
+                           int num_codebooks, int codebook_size, int hidden_channels, const float *embedding,
+                           float scale, float *act, void *stream);
+int mcq_jcl_hidden_backward(const float *grad_act, const float *act, const void *codes, int codes_dtype,
+                            int64_t num_frames, int num_codebooks, int codebook_size, int hidden_channels, float scale,
+                            float *grad_hidden, float *grad_embedding, void *stream);
+int mcq_jcl_partials(void);
+int mcq_jcl_cross_entropy(float *logits, const float *bias, const void *codes, int codes_dtype, int64_t num_frames,
+                          int num_codebooks, int codebook_size, int64_t ignore_index, int want_grad, float *row_loss,
+                          float *sums, float *partials, void *stream);
+
 /* Pointers into the prepared blob (device): scaled centers (N*K, D) fp32 and the Gram table (N*K, N*K). */
 const float *mcq_prepared_scaled_centers(const void *prepared, int num_codebooks, int codebook_size, int dim);
 const float *mcq_prepared_gram(const void *prepared, int num_codebooks, int codebook_size, int dim);

@@ -2,5 +2,6 @@
 danpovey/quantization, behind the reference's `Quantizer` / `QuantizerTrainer` API.  See DESIGN.md."""
 from .quantizer import Quantizer  # noqa: F401
 from .trainer import QuantizerTrainer  # noqa: F401
+from .prediction import JointCodebookLoss  # noqa: F401
 
-__all__ = ["Quantizer", "QuantizerTrainer"]
+__all__ = ["Quantizer", "QuantizerTrainer", "JointCodebookLoss"]

@@ -55,6 +55,10 @@ def lib():
         "mcq_xct": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, vp, sz, vp]),
         "mcq_search": (i32, [vp, vp, i64, i32, i32, i32, vp, vp, vp]),
         "mcq_encode_host": (i32, [vp, i32, i64, i32, i32, i32, vp, i32, vp, i32, i32]),
+        "mcq_jcl_hidden_forward": (i32, [vp, vp, i32, i64, i32, i32, i32, vp, f32, vp, vp]),
+        "mcq_jcl_hidden_backward": (i32, [vp, vp, vp, i32, i64, i32, i32, i32, f32, vp, vp, vp]),
+        "mcq_jcl_partials": (i32, []),
+        "mcq_jcl_cross_entropy": (i32, [vp, vp, vp, i32, i64, i32, i32, i64, i32, vp, vp, vp, vp]),
         "mcq_profile": (i32, [i32]),
         "mcq_profile_read": (i32, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     }
@@ -70,6 +74,7 @@ EXPORTS = ["mcq_version", "mcq_last_error", "mcq_packed_cols", "mcq_prepared_byt
            "mcq_prepare", "mcq_encode", "mcq_refine", "mcq_decode", "mcq_decode_centers", "mcq_decode_backward",
            "mcq_class_loss_forward", "mcq_class_loss_backward", "mcq_class_loss_partials",
            "mcq_prepared_scaled_centers", "mcq_prepared_gram", "mcq_xct", "mcq_search", "mcq_encode_host",
+           "mcq_jcl_hidden_forward", "mcq_jcl_hidden_backward", "mcq_jcl_partials", "mcq_jcl_cross_entropy",
            "mcq_profile", "mcq_profile_read"]
 
 

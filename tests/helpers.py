@@ -53,3 +53,29 @@ def search_supported(N, K):
     """(K, N) pairs the CUDA search kernels are built for: everything the reference itself supports up to
     codebook_size 256 and 64 codebooks (K < 16 with N > 1 crashes in the reference, quantization.py:453,470,504-507)."""
     return K <= 256 and N <= 64 and (N == 1 or K >= 16)
+
+
+_JCL_PARAM_ORDER = ("linear1.weight", "linear1.bias", "codebook_embedding.weight", "linear2_weight", "linear2b_weight",
+                    "linear2_bias")
+
+
+def jcl_golden():
+    """(arrays, meta) of tests/golden/golden_jcl.npz (made by tests/golden/make_golden_jcl.py from the reference)."""
+    import json
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_jcl.npz"))
+    meta = json.loads(bytes(g["meta_json"]).decode())
+    return g, meta
+
+
+def jcl_case_names():
+    return list(jcl_golden()[1].keys())
+
+
+def jcl_case(g, meta, name):
+    """Inputs of one golden JointCodebookLoss case as numpy arrays, flattened to (B, .)."""
+    m = meta[name]
+    par = {pn: g[f"{name}/param/{pn}"] for pn in _JCL_PARAM_ORDER}
+    grads = {pn: g[f"{name}/grad/{pn}"] for pn in _JCL_PARAM_ORDER}
+    pred = g[name + "/pred"].reshape(-1, m["P"])
+    codes = g[name + "/codes"].reshape(-1, m["N"])
+    return m, pred, codes, par, grads

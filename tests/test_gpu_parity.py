@@ -530,7 +530,8 @@ def test_encode_host_matches_device():
     assert torch.equal(q.encode_host(x), out)  # pageable host memory works too
 
 
-@pytest.mark.parametrize("K,N,B", [(16, 4, 512), (256, 4, 1000), (64, 2, 777), (32, 8, 130)])
+@pytest.mark.parametrize("K,N,B", [(16, 4, 512), (256, 4, 1000), (64, 2, 777), (32, 8, 130), (256, 32, 96), (16, 64, 100),
+                                   (256, 1, 300)])
 def test_compute_loss_and_gradients(K, N, B):
     """compute_loss values and gradients against a plain-PyTorch evaluation on the same indexes (K >= 32 goes
     through the fused classifier-loss kernels, mcq_class_loss_forward / _backward; K = 16 through PyTorch)."""
@@ -562,13 +563,14 @@ def test_compute_loss_and_gradients(K, N, B):
         assert torch.allclose(g_ours[n], v.grad, rtol=1e-4, atol=1e-7), n
 
 
-def test_trainer_runs_and_improves():
+@pytest.mark.parametrize("bpf", [1, 2, 32])  # the smallest and the largest bytes_per_frame the reference allows (:614)
+def test_trainer_runs_and_improves(bpf):
     import random
     from quantization_b200 import QuantizerTrainer
     torch.manual_seed(1)
     random.seed(1)
     dim = 64
-    tr = QuantizerTrainer(dim=dim, bytes_per_frame=2, device=DEV, phase_one_iters=60, phase_two_iters=60)
+    tr = QuantizerTrainer(dim=dim, bytes_per_frame=bpf, device=DEV, phase_one_iters=60, phase_two_iters=60)
     gen = torch.Generator().manual_seed(3)
     mix = torch.randn(dim, dim, generator=gen) / dim ** 0.5
     first = last = None
@@ -585,5 +587,5 @@ def test_trainer_runs_and_improves():
         steps += 1
     assert steps == 121  # p1 + p2 + 1, like the reference
     qf = tr.get_quantizer()
-    assert (qf.codebook_size, qf.num_codebooks) == (256, 2)
+    assert (qf.codebook_size, qf.num_codebooks) == (256, bpf)
     assert last < first

@@ -6,6 +6,7 @@ import torch
 
 import oracle
 from quantization_b200 import synth
+import helpers
 from helpers import case_inputs, golden_case_names, trained_params
 
 
@@ -90,3 +91,43 @@ def test_oracle_empty_batch():
                                  p["bias"].numpy())
     assert idx.shape == (0, 2)
     assert oracle.decode(np.zeros((0, 2), np.int64), p["centers"].numpy()).shape == (0, 32)
+
+
+# ---- JointCodebookLoss: the numpy restatement against the reference's own outputs ----
+
+@pytest.mark.parametrize("name", helpers.jcl_case_names())
+def test_jcl_oracle_matches_reference_golden(name):
+    from oracle import jcl_oracle as jo
+    g, meta = helpers.jcl_golden()
+    m, pred, codes, par, grads = helpers.jcl_case(g, meta, name)
+    args = (pred, codes, par["linear1.weight"], par["linear1.bias"], par["codebook_embedding.weight"],
+            par["linear2_weight"], par["linear2b_weight"], par["linear2_bias"])
+    loss = jo.joint_codebook_loss(*args, ignore_index=-100, reduction=m["reduction"])
+    ref = g[name + "/loss"].astype(np.float64)
+    assert np.allclose(loss, ref.reshape(np.shape(loss)), rtol=2e-6, atol=1e-6)
+    up = g[name + "/upstream"]
+    gr = jo.joint_codebook_loss_grads(*args, ignore_index=-100, reduction=m["reduction"], upstream=up)
+    pairs = [("pred", g[name + "/g_pred"].reshape(pred.shape)), ("w1", grads["linear1.weight"]),
+             ("b1", grads["linear1.bias"]), ("emb", grads["codebook_embedding.weight"]), ("w2", grads["linear2_weight"]),
+             ("w2b", grads["linear2b_weight"]), ("bias2", grads["linear2_bias"])]
+    for k, ref_g in pairs:
+        scale = np.abs(ref_g).max() + 1e-30
+        assert np.abs(gr[k] - ref_g).max() <= 2e-5 * scale, k
+
+
+def test_jcl_hidden_stage_is_the_reference_order():
+    """The fp32 stage restatement (what the CUDA kernel is compared with bit for bit) against the fp64 one."""
+    from oracle import jcl_oracle as jo
+    g, meta = helpers.jcl_golden()
+    for name in helpers.jcl_case_names():
+        m, pred, codes, par, _ = helpers.jcl_case(g, meta, name)
+        hidden = (pred.astype(np.float64) @ par["linear1.weight"].astype(np.float64).T
+                  + par["linear1.bias"]).astype(np.float32)
+        act = jo.hidden_stage(hidden, codes, par["codebook_embedding.weight"], m["K"])
+        # same stage in fp64 started from the same hidden vector
+        first = np.maximum(codes[:, :-1], 0) + np.arange(m["N"] - 1) * m["K"]
+        e = par["codebook_embedding.weight"].astype(np.float64)[first] * jo.embedding_scale(m["H"], m["N"])
+        pre = np.cumsum(np.concatenate([hidden.astype(np.float64)[:, None, :], e], axis=1), axis=1)
+        ref = np.maximum(pre, 0).transpose(1, 0, 2)
+        assert act.shape == ref.shape and act.dtype == np.float32
+        assert np.abs(act - ref).max() <= 1e-5 * (np.abs(ref).max() + 1e-30)
