@@ -121,6 +121,19 @@ int mcq_class_loss_backward(const float *xw, int64_t num_frames, int dim, int nu
                             const float *g_prob_sum, float *grad_logits, float *part_gx, void *stream);
 
 /*
+ * Weight-gradient product: out (c1, c2) = a^T . b, reduction over `rows` frames; a (rows, c1) fp32 with row stride lda,
+ * b (rows, c2) fp32 / fp16 / bf16 with row stride ldb (elements).  This is what the reference's autograd computes with
+ * an fp32 SGEMM for d loss / d to_logits.weight (backward of quantization.py:279) and for the linear1 / linear2 /
+ * linear2b weights of JointCodebookLoss (backward of prediction.py:56, :70-76).  Here: transposing fp16x2 split of both
+ * operands, split-K tcgen05 product with fp32 accumulation, fixed-order sum of the partial products (reproducible;
+ * error <= 2^-18 sum_r |a_r b_r| per output, measured ~2^-20:
+ * the class of an fp32 SGEMM over as many rows).  workspace: mcq_gemm_tn_workspace_bytes(rows, c1, c2) bytes.
+ */
+size_t mcq_gemm_tn_workspace_bytes(int64_t rows, int c1, int c2);
+int mcq_gemm_tn(const float *a, int64_t lda, const void *b, int b_dtype, int64_t ldb, int64_t rows, int c1, int c2,
+                float *out, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
  * JointCodebookLoss (reference prediction.py:9-82, class :86-197): the stages between its dense products.
  * Layouts: hidden / grad_hidden (B, H) fp32 = linear1(predictor); codes (B, N) uint8 / int32 / int64 as produced by
  * mcq_encode (negative = padding where the type allows it); embedding ((N-1)*K, H) fp32 = codebook_embedding.weight;

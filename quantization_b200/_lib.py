@@ -55,6 +55,8 @@ def lib():
         "mcq_xct": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, vp, sz, vp]),
         "mcq_search": (i32, [vp, vp, i64, i32, i32, i32, vp, vp, vp]),
         "mcq_encode_host": (i32, [vp, i32, i64, i32, i32, i32, vp, i32, vp, i32, i32]),
+        "mcq_gemm_tn_workspace_bytes": (sz, [i64, i32, i32]),
+        "mcq_gemm_tn": (i32, [vp, i64, vp, i32, i64, i64, i32, i32, vp, vp, sz, vp]),
         "mcq_jcl_hidden_forward": (i32, [vp, vp, i32, i64, i32, i32, i32, vp, f32, vp, vp]),
         "mcq_jcl_hidden_backward": (i32, [vp, vp, vp, i32, i64, i32, i32, i32, f32, vp, vp, vp]),
         "mcq_jcl_partials": (i32, []),
@@ -74,7 +76,7 @@ EXPORTS = ["mcq_version", "mcq_last_error", "mcq_packed_cols", "mcq_prepared_byt
            "mcq_prepare", "mcq_encode", "mcq_refine", "mcq_decode", "mcq_decode_centers", "mcq_decode_backward",
            "mcq_class_loss_forward", "mcq_class_loss_backward", "mcq_class_loss_partials",
            "mcq_prepared_scaled_centers", "mcq_prepared_gram", "mcq_xct", "mcq_search", "mcq_encode_host",
-           "mcq_jcl_hidden_forward", "mcq_jcl_hidden_backward", "mcq_jcl_partials", "mcq_jcl_cross_entropy",
+           "mcq_gemm_tn_workspace_bytes", "mcq_gemm_tn", "mcq_jcl_hidden_forward", "mcq_jcl_hidden_backward", "mcq_jcl_partials", "mcq_jcl_cross_entropy",
            "mcq_profile", "mcq_profile_read"]
 
 
@@ -121,3 +123,22 @@ def profile_read():
     n = (ctypes.c_int64 * 4)()
     check(lib().mcq_profile_read(ms, n), "mcq_profile_read")
     return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(PROF_KINDS)}
+
+
+def gemm_tn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a^T . b on the tensor cores (include/mcq.h: mcq_gemm_tn): a (R, C1) fp32 (a column slice of a row-major matrix is
+    fine: stride(1) == 1), b (R, C2) fp32 / fp16 / bf16 -> (C1, C2) fp32."""
+    L = lib()
+    assert a.dtype == torch.float32 and a.dim() == 2 and b.dim() == 2 and a.shape[0] == b.shape[0]
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    R, C1 = a.shape
+    C2 = b.shape[1]
+    out = torch.empty(C1, C2, dtype=torch.float32, device=a.device)
+    if R == 0:
+        return out.zero_()
+    nbytes = L.mcq_gemm_tn_workspace_bytes(R, C1, C2)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+    with torch.cuda.device(a.device):
+        check(L.mcq_gemm_tn(a.data_ptr(), a.stride(0), b.data_ptr(), x_dtype_code(b), b.stride(0), R, C1, C2,
+                            out.data_ptr(), ws.data_ptr(), nbytes, stream_ptr(a.device)), "mcq_gemm_tn")
+    return out

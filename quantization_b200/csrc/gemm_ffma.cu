@@ -114,9 +114,47 @@ __global__ void argmax_init_kernel(const float *__restrict__ logits, const float
     }
 }
 
+// Small codebooks (K = 16 or 32: trainer phase 1): one thread per (frame, codebook) pair, the K logits are K*4
+// contiguous bytes read as float4 -- a warp per pair would leave half the lanes idle and spend its time in shuffles.
+template <int K>
+__global__ void __launch_bounds__(256) argmax_small_kernel(const float *__restrict__ logits, const float *__restrict__ bias,
+                                                           int64_t items, int N, int32_t *__restrict__ idx) {
+    for (int64_t item = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; item < items;
+         item += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(item % N);
+        const float4 *row = reinterpret_cast<const float4 *>(logits + (size_t)item * K);
+        const float4 *bs = reinterpret_cast<const float4 *>(bias + (size_t)n * K);
+        float best = 0.f;
+        int bk = 0;
+#pragma unroll
+        for (int q = 0; q < K / 4; ++q) {
+            const float4 v = __ldcs(row + q);
+            const float4 c = __ldg(bs + q);
+            const float e[4] = {v.x + c.x, v.y + c.y, v.z + c.z, v.w + c.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if ((q == 0 && t == 0) || e[t] > best) {  // strict >: first maximum on ties
+                    best = e[t];
+                    bk = q * 4 + t;
+                }
+        }
+        idx[item] = bk;
+    }
+}
+
 int launch_argmax_init(const float *logits, const float *bias, int64_t B, int N, int K, int32_t *idx, cudaStream_t st) {
     if (B <= 0) return MCQ_OK;
     int64_t items = B * N;
+    if (K == 16 || K == 32) {
+        int64_t blocks = (items + 255) / 256;
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        if (K == 16)
+            argmax_small_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(logits, bias, items, N, idx);
+        else
+            argmax_small_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(logits, bias, items, N, idx);
+        MCQ_LAUNCH_CHECK("argmax_small_kernel");
+        return MCQ_OK;
+    }
     int64_t blocks = (items + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
     argmax_init_kernel<<<(unsigned)blocks, 256, 0, st>>>(logits, bias, B, N, K, idx);

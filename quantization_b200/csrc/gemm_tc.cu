@@ -126,7 +126,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_fp16x2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                    float *__restrict__ C, int m_tiles, int n_tiles, int k_blocks, int ldc, int a_plane_rows,
                    int b_plane_rows, const float *__restrict__ a_scale, const float *__restrict__ b_scale,
-                   const float *__restrict__ bias, float *__restrict__ part_val, int *__restrict__ part_idx) {
+                   const float *__restrict__ bias, float *__restrict__ part_val, int *__restrict__ part_idx,
+                   int k_splits, size_t c_split_stride) {
+    // k_splits > 1 (split-K, for products with few output tiles and a long reduction): tile t covers k-blocks
+    // [ks * k_blocks, (ks + 1) * k_blocks) with ks = t / (m_tiles * n_tiles) and stores into C + ks * c_split_stride;
+    // the caller sums the k_splits partial results in a fixed order.
     using Cfg = TcCfg<BN>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -141,7 +145,8 @@ gemm_fp16x2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = m_tiles * n_tiles;
+    const int mn_tiles = m_tiles * n_tiles;
+    const int num_tiles = mn_tiles * k_splits;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -173,15 +178,16 @@ gemm_fp16x2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             int s = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+                const int mn = tile % mn_tiles, kb0 = (tile / mn_tiles) * k_blocks;
+                const int m0 = (mn / n_tiles) * BM, n0 = (mn % n_tiles) * BN;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t st = base + s * Cfg::STAGE;
                     mbar_expect_tx(full_bar(s), Cfg::STAGE);
 #pragma unroll
                     for (int p = 0; p < PLANES; ++p) {
-                        tma_load_2d(st + p * Cfg::A_PLANE, &tma_a, kb * BK, p * a_plane_rows + m0, full_bar(s));
-                        tma_load_2d(st + PLANES * Cfg::A_PLANE + p * Cfg::B_PLANE, &tma_b, kb * BK,
+                        tma_load_2d(st + p * Cfg::A_PLANE, &tma_a, (kb0 + kb) * BK, p * a_plane_rows + m0, full_bar(s));
+                        tma_load_2d(st + PLANES * Cfg::A_PLANE + p * Cfg::B_PLANE, &tma_b, (kb0 + kb) * BK,
                                     p * b_plane_rows + n0, full_bar(s));
                     }
                     if (++s == STAGES) {
@@ -240,10 +246,11 @@ gemm_fp16x2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         int acc = 0;
         uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+            const int mn = tile % mn_tiles;
+            const int m0 = (mn / n_tiles) * BM, n0 = (mn % n_tiles) * BN;
+            float *Ct = C + (size_t)(tile / mn_tiles) * c_split_stride;
             mbar_wait(tfull_bar(acc), aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float *crow = C + (size_t)(m0 + q * 32 + lane) * ldc + n0;
             const float sa = __ldg(a_scale + m0 + q * 32 + lane);  // 2^-e of my row of A
             float best = 0.0f;
             int bk = -1;
@@ -281,7 +288,7 @@ gemm_fp16x2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                         *reinterpret_cast<float4 *>(stg + lane * 36 + 4 * v) = o;
                     }
                     __syncwarp();
-                    float *cbase = C + (size_t)(m0 + q * 32) * ldc + n0 + c * 32 + (lane & 7) * 4;
+                    float *cbase = Ct + (size_t)(m0 + q * 32) * ldc + n0 + c * 32 + (lane & 7) * 4;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int row = k * 4 + (lane >> 3);
@@ -355,7 +362,7 @@ int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint
 template <int BN, bool ARGMAX>
 int launch_bn(const __half *a_split, const float *a_scale, const __half *b_split, const float *b_scale, float *C,
               int64_t Mp, int NK, int Dp, cudaStream_t st, const float *bias = nullptr, float *part_val = nullptr,
-              int *part_idx = nullptr) {
+              int *part_idx = nullptr, int k_splits = 1) {
     using Cfg = TcCfg<BN>;
     const uint64_t NKp = align_up((size_t)NK, 128);
     CUtensorMap ma, mb;
@@ -368,10 +375,10 @@ int launch_bn(const __half *a_split, const float *a_scale, const __half *b_split
     MCQ_CUDA(cudaGetDevice(&dev));
     MCQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int m_tiles = (int)(Mp / BM), n_tiles = NK / BN;
-    int64_t tiles = (int64_t)m_tiles * n_tiles;
+    int64_t tiles = (int64_t)m_tiles * n_tiles * k_splits;
     int grid = (int)(tiles < sms ? tiles : sms);
-    kern<<<grid, NUM_THREADS, Cfg::SMEM, st>>>(ma, mb, C, m_tiles, n_tiles, Dp / BK, NK, (int)Mp, (int)NKp, a_scale, b_scale,
-                                               bias, part_val, part_idx);
+    kern<<<grid, NUM_THREADS, Cfg::SMEM, st>>>(ma, mb, C, m_tiles, n_tiles, Dp / BK / k_splits, NK, (int)Mp, (int)NKp, a_scale,
+                                               b_scale, bias, part_val, part_idx, k_splits, (size_t)Mp * (size_t)NK);
     MCQ_LAUNCH_CHECK("gemm_fp16x2_kernel");
     return MCQ_OK;
 }
@@ -387,6 +394,20 @@ int launch_gemm_tc(const __half *a_split, const float *a_scale, const __half *b_
     }
     if (NK % 128 == 0) return launch_bn<128, false>(a_split, a_scale, b_split, b_scale, C, Mp, NK, Dp, st);
     return launch_bn<64, false>(a_split, a_scale, b_split, b_scale, C, Mp, NK, Dp, st);
+}
+
+// Split-K variant: `k_splits` partial products C[ks] (each Mp x NK, contiguous) over Dp / k_splits columns each.
+int launch_gemm_tc_splitk(const __half *a_split, const float *a_scale, const __half *b_split, const float *b_scale,
+                          float *C, int64_t Mp, int NK, int Dp, int k_splits, cudaStream_t st) {
+    if (Mp <= 0) return MCQ_OK;
+    if (Mp % BM != 0 || k_splits < 1 || Dp % (BK * k_splits) != 0 || NK % 64 != 0) {
+        set_error("gemm_tc_splitk: Mp=%lld Dp=%d NK=%d splits=%d not tile aligned", (long long)Mp, Dp, NK, k_splits);
+        return MCQ_EINVAL;
+    }
+    if (NK % 128 == 0)
+        return launch_bn<128, false>(a_split, a_scale, b_split, b_scale, C, Mp, NK, Dp, st, nullptr, nullptr, nullptr,
+                                     k_splits);
+    return launch_bn<64, false>(a_split, a_scale, b_split, b_scale, C, Mp, NK, Dp, st, nullptr, nullptr, nullptr, k_splits);
 }
 
 // idx[b][n] = first maximum over the K / 128 tile maxima of codebook n (ascending tile = ascending column order)

@@ -11,7 +11,8 @@ Same constructor arguments, parameter names (`linear1`, `codebook_embedding`, `l
   * the cross entropy (:79-82) is one kernel (`mcq_jcl_cross_entropy`) that also leaves softmax - onehot in place of the
     logits, so the backward pass starts from it with no log-softmax graph;
   * the backward of the gather/cumsum/ReLU stage is one kernel (`mcq_jcl_hidden_backward`);
-  * the dense products are plain fp32 library GEMMs (cuBLAS through torch.mm / torch.bmm), as in the reference.
+  * the weight gradients (reductions over all frames) are split-K tcgen05 products (`mcq_gemm_tn`, fp32-faithful fp16x2
+    split); the remaining dense products are plain fp32 library GEMMs (cuBLAS through torch.mm / torch.bmm).
 
 `checkpoint=True` keeps the reference's meaning (prediction.py:113-115: recompute in backward, store only the inputs).
 The codes may be the uint8 tensor `Quantizer.encode` returns (no int64 copy is made), int32 or int64 (negative =
@@ -98,12 +99,13 @@ class _JointCodebookLossFn(torch.autograd.Function):
             _lib.check(L.mcq_jcl_hidden_backward(grad_act.data_ptr(), act.data_ptr(), codes.data_ptr(),
                                                  _lib.idx_dtype_code(codes), B, N, K, H, scale, grad_hidden.data_ptr(),
                                                  grad_emb.data_ptr(), _lib.stream_ptr(dev)), "mcq_jcl_hidden_backward")
-        grad_w2 = torch.bmm(dlv.transpose(1, 2), act)  # (N, K, H)
-        grad_w2b = dl.t().mm(pred).view(N, K, P)
+        # weight gradients: reductions over the frames -> split-K tcgen05 products (mcq_gemm_tn)
+        grad_w2 = torch.stack([_lib.gemm_tn(dl[:, n * K:(n + 1) * K], act[n]) for n in range(N)])  # (N, K, H)
+        grad_w2b = _lib.gemm_tn(dl, pred).view(N, K, P)
         grad_bias2 = dl.sum(dim=0).view(N, K)
         grad_pred = dl.mm(w2b.reshape(N * K, P))
         grad_pred.addmm_(grad_hidden, w1)
-        grad_w1 = grad_hidden.t().mm(pred)
+        grad_w1 = _lib.gemm_tn(grad_hidden, pred)
         grad_b1 = grad_hidden.sum(dim=0) if has_b1 else None
         if gs is not None:  # everything above is linear in dl: scale the (small) results instead of the (B, N*K) tensor
             grad_pred, grad_w1, grad_emb, grad_w2, grad_w2b, grad_bias2 = (

@@ -99,8 +99,9 @@ class _ClassLossFn(torch.autograd.Function):
                                            part_gx.data_ptr(), _lib.stream_ptr(x.device))
         _lib.check(rc, "mcq_class_loss_backward")
         scale = (logits_scale.detach() * q.scale_speed).exp()
-        xs = scale * x.float()                       # what the reference feeds to_logits (quantization.py:278)
-        grad_w = grad_logits.t().mm(xs)              # (N*K, D)
+        # d loss / d weight = grad_logits^T . (scale * x)  (backward of quantization.py:278-279): split-K tcgen05
+        # product over the frames (mcq_gemm_tn), the scalar applied to the (N*K, D) result
+        grad_w = _lib.gemm_tn(grad_logits, x) * scale
         grad_b = grad_logits.sum(dim=0)
         # d/d logits_scale: logits = xs W^T + b with d xs / d logits_scale = speed * xs, so the gradient is
         # speed * sum(grad_logits * (xs W^T)); xs W^T is the saved forward product and the kernel above already

@@ -592,3 +592,28 @@ def test_trainer_runs_and_improves(bpf):
     qf = tr.get_quantizer()
     assert (qf.codebook_size, qf.num_codebooks) == (256, bpf)
     assert last < first
+
+
+@pytest.mark.parametrize("R,C1,C2,dt", [(70000, 1024, 256, torch.bfloat16), (65536, 128, 256, torch.float32),
+                                        (3000, 40, 40, torch.float32), (777, 256, 96, torch.float16),
+                                        (100, 16, 8, torch.float32), (20000, 300, 520, torch.float32)])
+def test_gemm_tn_split_k(R, C1, C2, dt):
+    """mcq_gemm_tn (weight-gradient product a^T . b, split-K tcgen05 with fp16x2 operands) against fp64: the error of
+    every output is bounded by 2^-18 * sum_r |a_r b_r| (the bound stated in include/mcq.h; an fp32 SGEMM over as many
+    rows is in the same class; the measured worst ratio is recorded), entries spanning many orders of magnitude, `a` a column slice of a wider matrix; bitwise reproducible."""
+    gen = torch.Generator().manual_seed(R + C1)
+    wide = torch.randn(R, C1 + 24, generator=gen) * torch.exp(3 * torch.randn(R, 1, generator=gen))
+    b = (torch.randn(R, C2, generator=gen) * torch.exp(2 * torch.randn(1, C2, generator=gen))).to(dt)
+    wd, bd = wide.to(DEV), b.to(DEV)
+    a = wd[:, 8:8 + C1]
+    out = _lib.gemm_tn(a, bd)
+    out2 = _lib.gemm_tn(a, bd)
+    assert torch.equal(out, out2)
+    a64, b64 = a.double(), bd.double()
+    ref = a64.t().mm(b64)
+    mag = a64.abs().t().mm(b64.abs()) + 1e-300
+    worst = ((out.double() - ref).abs() / mag).max().item()
+    sgemm = ((a.t().mm(bd.float()).double() - ref).abs() / mag).max().item()  # the library fp32 product, for scale
+    _record("gemm_tn", f"{R}x{C1}x{C2}", {"worst_err_over_sum_abs": worst, "log2": float(np.log2(worst + 1e-300)),
+                                         "library_sgemm_log2": float(np.log2(sgemm + 1e-300))})
+    assert worst <= 2.0 ** -18, np.log2(worst)
