@@ -134,6 +134,17 @@ int mcq_gemm_tn(const float *a, int64_t lda, const void *b, int b_dtype, int64_t
                 float *out, void *workspace, size_t workspace_bytes, void *stream);
 
 /*
+ * out (m, n) = or += a . b^T: a (m, k) fp32 row stride lda, b (n, k) fp32 row stride ldb, out row stride ldc (a column
+ * block of a wider matrix is fine).  The forward / input-gradient products of JointCodebookLoss (prediction.py:56,
+ * :70-76 and their backward) -- fp32 SGEMMs in the reference -- as fp32-faithful tcgen05 products: per-row power-of-two
+ * scaling, fp16x2 split, three products accumulated in fp32 (the scheme of the encode path).  n must be a multiple of
+ * 64, ldc of 4, out 16-byte aligned (MCQ_EUNSUPPORTED otherwise: the host layer then uses a library GEMM).
+ */
+size_t mcq_gemm_nt_workspace_bytes(int64_t m, int n, int k);
+int mcq_gemm_nt(const float *a, int64_t lda, const float *b, int64_t ldb, int64_t m, int n, int k, float *out,
+                int64_t ldc, int accumulate, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
  * JointCodebookLoss (reference prediction.py:9-82, class :86-197): the stages between its dense products.
  * Layouts: hidden / grad_hidden (B, H) fp32 = linear1(predictor); codes (B, N) uint8 / int32 / int64 as produced by
  * mcq_encode (negative = padding where the type allows it); embedding ((N-1)*K, H) fp32 = codebook_embedding.weight;

@@ -57,6 +57,8 @@ def lib():
         "mcq_encode_host": (i32, [vp, i32, i64, i32, i32, i32, vp, i32, vp, i32, i32]),
         "mcq_gemm_tn_workspace_bytes": (sz, [i64, i32, i32]),
         "mcq_gemm_tn": (i32, [vp, i64, vp, i32, i64, i64, i32, i32, vp, vp, sz, vp]),
+        "mcq_gemm_nt_workspace_bytes": (sz, [i64, i32, i32]),
+        "mcq_gemm_nt": (i32, [vp, i64, vp, i64, i64, i32, i32, vp, i64, i32, vp, sz, vp]),
         "mcq_jcl_hidden_forward": (i32, [vp, vp, i32, i64, i32, i32, i32, vp, f32, vp, vp]),
         "mcq_jcl_hidden_backward": (i32, [vp, vp, vp, i32, i64, i32, i32, i32, f32, vp, vp, vp]),
         "mcq_jcl_partials": (i32, []),
@@ -76,7 +78,8 @@ EXPORTS = ["mcq_version", "mcq_last_error", "mcq_packed_cols", "mcq_prepared_byt
            "mcq_prepare", "mcq_encode", "mcq_refine", "mcq_decode", "mcq_decode_centers", "mcq_decode_backward",
            "mcq_class_loss_forward", "mcq_class_loss_backward", "mcq_class_loss_partials",
            "mcq_prepared_scaled_centers", "mcq_prepared_gram", "mcq_xct", "mcq_search", "mcq_encode_host",
-           "mcq_gemm_tn_workspace_bytes", "mcq_gemm_tn", "mcq_jcl_hidden_forward", "mcq_jcl_hidden_backward", "mcq_jcl_partials", "mcq_jcl_cross_entropy",
+           "mcq_gemm_tn_workspace_bytes", "mcq_gemm_tn", "mcq_gemm_nt_workspace_bytes", "mcq_gemm_nt",
+           "mcq_jcl_hidden_forward", "mcq_jcl_hidden_backward", "mcq_jcl_partials", "mcq_jcl_cross_entropy",
            "mcq_profile", "mcq_profile_read"]
 
 
@@ -141,4 +144,29 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(a.device):
         check(L.mcq_gemm_tn(a.data_ptr(), a.stride(0), b.data_ptr(), x_dtype_code(b), b.stride(0), R, C1, C2,
                             out.data_ptr(), ws.data_ptr(), nbytes, stream_ptr(a.device)), "mcq_gemm_tn")
+    return out
+
+
+def gemm_nt_supported(a: torch.Tensor, b: torch.Tensor) -> bool:
+    """Shapes the tcgen05 product takes (others go to a library GEMM in the host layer)."""
+    return b.shape[0] % 64 == 0 and a.shape[0] >= 256
+
+
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor = None, accumulate: bool = False) -> torch.Tensor:
+    """a . b^T on the tensor cores (include/mcq.h: mcq_gemm_nt): a (M, K), b (N, K) fp32 with unit inner stride (row
+    slices / column blocks of wider matrices are fine) -> out (M, N) fp32, which may itself be a column block."""
+    L = lib()
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.shape[1] == b.shape[1]
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    M, K = a.shape
+    N = b.shape[0]
+    if out is None:
+        assert not accumulate
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype == torch.float32
+    nbytes = L.mcq_gemm_nt_workspace_bytes(M, N, K)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+    with torch.cuda.device(a.device):
+        check(L.mcq_gemm_nt(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), M, N, K, out.data_ptr(), out.stride(0),
+                            int(accumulate), ws.data_ptr(), nbytes, stream_ptr(a.device)), "mcq_gemm_nt")
     return out

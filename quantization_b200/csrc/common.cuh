@@ -81,6 +81,9 @@ int launch_gemm_tc(const __half *a_split, const float *a_scale, const __half *b_
 bool gemm_tc_argmax_supported(int NK, int K);
 int launch_gemm_tc_splitk(const __half *a_split, const float *a_scale, const __half *b_split, const float *b_scale,
                           float *C, int64_t Mp, int NK, int Dp, int k_splits, cudaStream_t st);
+int launch_gemm_tc_general(const __half *a_split, const float *a_scale, const __half *b_split, const float *b_scale,
+                           float *C, int64_t ldc, int64_t m_valid, int64_t Mp, int NK, int Dp, int accumulate,
+                           cudaStream_t st);
 int launch_gemm_tc_argmax(const __half *a_split, const float *a_scale, const __half *b_split, const float *b_scale,
                           int64_t Mp, int NK, int Dp, const float *bias, int64_t B, int N, int K, void *scratch,
                           int32_t *idx, cudaStream_t st);

@@ -127,7 +127,8 @@ gemm_fp16x2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                    float *__restrict__ C, int m_tiles, int n_tiles, int k_blocks, int ldc, int a_plane_rows,
                    int b_plane_rows, const float *__restrict__ a_scale, const float *__restrict__ b_scale,
                    const float *__restrict__ bias, float *__restrict__ part_val, int *__restrict__ part_idx,
-                   int k_splits, size_t c_split_stride) {
+                   int k_splits, size_t c_split_stride, int m_valid, int accumulate) {
+    // m_valid: rows >= m_valid of the (padded) product are not stored; accumulate != 0: C += product.
     // k_splits > 1 (split-K, for products with few output tiles and a long reduction): tile t covers k-blocks
     // [ks * k_blocks, (ks + 1) * k_blocks) with ks = t / (m_tiles * n_tiles) and stores into C + ks * c_split_stride;
     // the caller sums the k_splits partial results in a fixed order.
@@ -289,11 +290,22 @@ gemm_fp16x2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     }
                     __syncwarp();
                     float *cbase = Ct + (size_t)(m0 + q * 32) * ldc + n0 + c * 32 + (lane & 7) * 4;
+                    const int rows_left = m_valid - (m0 + q * 32);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int row = k * 4 + (lane >> 3);
-                        const float4 o = *reinterpret_cast<const float4 *>(stg + row * 36 + (lane & 7) * 4);
-                        *reinterpret_cast<float4 *>(cbase + (size_t)row * ldc) = o;
+                        float4 o = *reinterpret_cast<const float4 *>(stg + row * 36 + (lane & 7) * 4);
+                        if (row < rows_left) {
+                            float4 *dst = reinterpret_cast<float4 *>(cbase + (size_t)row * ldc);
+                            if (accumulate) {
+                                const float4 old = *dst;
+                                o.x += old.x;
+                                o.y += old.y;
+                                o.z += old.z;
+                                o.w += old.w;
+                            }
+                            *dst = o;
+                        }
                     }
                     __syncwarp();
                 }
@@ -362,7 +374,7 @@ int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint
 template <int BN, bool ARGMAX>
 int launch_bn(const __half *a_split, const float *a_scale, const __half *b_split, const float *b_scale, float *C,
               int64_t Mp, int NK, int Dp, cudaStream_t st, const float *bias = nullptr, float *part_val = nullptr,
-              int *part_idx = nullptr, int k_splits = 1) {
+              int *part_idx = nullptr, int k_splits = 1, int64_t ldc = 0, int64_t m_valid = -1, int accumulate = 0) {
     using Cfg = TcCfg<BN>;
     const uint64_t NKp = align_up((size_t)NK, 128);
     CUtensorMap ma, mb;
@@ -377,8 +389,9 @@ int launch_bn(const __half *a_split, const float *a_scale, const __half *b_split
     const int m_tiles = (int)(Mp / BM), n_tiles = NK / BN;
     int64_t tiles = (int64_t)m_tiles * n_tiles * k_splits;
     int grid = (int)(tiles < sms ? tiles : sms);
-    kern<<<grid, NUM_THREADS, Cfg::SMEM, st>>>(ma, mb, C, m_tiles, n_tiles, Dp / BK / k_splits, NK, (int)Mp, (int)NKp, a_scale,
-                                               b_scale, bias, part_val, part_idx, k_splits, (size_t)Mp * (size_t)NK);
+    kern<<<grid, NUM_THREADS, Cfg::SMEM, st>>>(ma, mb, C, m_tiles, n_tiles, Dp / BK / k_splits, ldc > 0 ? (int)ldc : NK,
+                                               (int)Mp, (int)NKp, a_scale, b_scale, bias, part_val, part_idx, k_splits,
+                                               (size_t)Mp * (size_t)NK, m_valid >= 0 ? (int)m_valid : (int)Mp, accumulate);
     MCQ_LAUNCH_CHECK("gemm_fp16x2_kernel");
     return MCQ_OK;
 }
@@ -408,6 +421,22 @@ int launch_gemm_tc_splitk(const __half *a_split, const float *a_scale, const __h
         return launch_bn<128, false>(a_split, a_scale, b_split, b_scale, C, Mp, NK, Dp, st, nullptr, nullptr, nullptr,
                                      k_splits);
     return launch_bn<64, false>(a_split, a_scale, b_split, b_scale, C, Mp, NK, Dp, st, nullptr, nullptr, nullptr, k_splits);
+}
+
+// General form: C (m_valid x NK, row stride ldc) = or += A . B^T from packed operands (Mp = m_valid rounded up to 128).
+int launch_gemm_tc_general(const __half *a_split, const float *a_scale, const __half *b_split, const float *b_scale,
+                           float *C, int64_t ldc, int64_t m_valid, int64_t Mp, int NK, int Dp, int accumulate,
+                           cudaStream_t st) {
+    if (Mp <= 0) return MCQ_OK;
+    if (Mp % BM != 0 || Dp % BK != 0 || NK % 64 != 0 || ldc < NK || (ldc & 3) || m_valid > Mp) {
+        set_error("gemm_tc_general: Mp=%lld Dp=%d NK=%d ldc=%lld not supported", (long long)Mp, Dp, NK, (long long)ldc);
+        return MCQ_EINVAL;
+    }
+    if (NK % 128 == 0)
+        return launch_bn<128, false>(a_split, a_scale, b_split, b_scale, C, Mp, NK, Dp, st, nullptr, nullptr, nullptr, 1,
+                                     ldc, m_valid, accumulate);
+    return launch_bn<64, false>(a_split, a_scale, b_split, b_scale, C, Mp, NK, Dp, st, nullptr, nullptr, nullptr, 1, ldc,
+                                m_valid, accumulate);
 }
 
 // idx[b][n] = first maximum over the K / 128 tile maxima of codebook n (ascending tile = ascending column order)

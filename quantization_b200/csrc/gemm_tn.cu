@@ -104,6 +104,69 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float *__restr
     }
 }
 
+// Non-transposing pack for products with the reduction along the rows' own elements (out = A . B^T):
+// planes[p][r][c] (r < Rp, c < Cp) = fp16 pieces of 2^e_r * X[r][c], inv_scale[r] = 2^-e_r with e_r from the row's
+// largest magnitude (the same per-row scaling as the encode path, prepare.cu); zero outside the matrix.  Warp per row.
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float *__restrict__ X, int64_t R, int C, int64_t ld,
+                                                        __half *__restrict__ planes, float *__restrict__ inv_scale,
+                                                        int64_t Rp, int Cp) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const size_t plane = (size_t)Rp * (size_t)Cp;
+    for (int64_t r = warp; r < Rp; r += nwarps) {
+        const float *row = X + (size_t)r * ld;
+        float m = 0.0f;
+        if (r < R)
+            for (int c = lane; c < C; c += 32) m = fmaxf(m, fabsf(row[c]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+        const float s = scale_for(__float_as_uint(m));
+        if (lane == 0) inv_scale[r] = 1.0f / s;
+        __half *h0 = planes + (size_t)r * Cp, *h1 = h0 + plane;
+        for (int c = 2 * lane; c < Cp; c += 64) {  // two columns per lane: 4-byte stores
+            float v0 = 0.0f, v1 = 0.0f;
+            if (r < R) {
+                if (c < C) v0 = row[c] * s;
+                if (c + 1 < C) v1 = row[c + 1] * s;
+            }
+            const __half a0 = __float2half_rn(v0), b0 = __float2half_rn(v1);
+            const __half a1 = __float2half_rn(v0 - __half2float(a0)), b1 = __float2half_rn(v1 - __half2float(b0));
+            *reinterpret_cast<__half2 *>(h0 + c) = __halves2half2(a0, b0);
+            *reinterpret_cast<__half2 *>(h1 + c) = __halves2half2(a1, b1);
+        }
+    }
+}
+
+int launch_pack_rows(const float *X, int64_t R, int C, int64_t ld, __half *planes, float *inv_scale, int64_t Rp, int Cp,
+                     cudaStream_t st) {
+    int64_t blocks = (Rp + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pack_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, R, C, ld, planes, inv_scale, Rp, Cp);
+    MCQ_LAUNCH_CHECK("pack_rows_kernel");
+    return MCQ_OK;
+}
+
+struct NtPlan {
+    int64_t Mp;
+    int Np, Kp;
+    size_t off_pa, off_pb, off_sa, off_sb, bytes;
+};
+
+NtPlan nt_plan(int64_t m, int n, int k) {
+    NtPlan p;
+    p.Mp = (int64_t)align_up((size_t)m, 128);
+    p.Np = (int)align_up((size_t)n, 128);  // rows of a plane of B (the tile loader reads whole 64/128-row boxes)
+    p.Kp = (int)align_up((size_t)k, 64);
+    size_t o = 0;
+    p.off_pa = o; o += align_up((size_t)2 * p.Mp * p.Kp * sizeof(__half), 1024);
+    p.off_pb = o; o += align_up((size_t)2 * p.Np * p.Kp * sizeof(__half), 1024);
+    p.off_sa = o; o += align_up((size_t)p.Mp * sizeof(float), 1024);
+    p.off_sb = o; o += align_up((size_t)p.Np * sizeof(float), 1024);
+    p.bytes = o;
+    return p;
+}
+
 struct TnPlan {
     int C1p, C2p, splits;
     int64_t Rp;
@@ -216,6 +279,42 @@ int mcq_gemm_tn(const float *a, int64_t lda, const void *b, int b_dtype, int64_t
     splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(part, p.splits, (size_t)p.C1p * p.C2p, p.C2p, c1, c2, out);
     MCQ_LAUNCH_CHECK("splitk_reduce_kernel");
     return MCQ_OK;
+}
+
+size_t mcq_gemm_nt_workspace_bytes(int64_t m, int n, int k) {
+    if (m <= 0 || n <= 0 || k <= 0) return 0;
+    return nt_plan(m, n, k).bytes;
+}
+
+int mcq_gemm_nt(const float *a, int64_t lda, const float *b, int64_t ldb, int64_t m, int n, int k, float *out,
+                int64_t ldc, int accumulate, void *workspace, size_t workspace_bytes, void *stream) {
+    if (m <= 0 || n <= 0 || k <= 0 || lda < k || ldb < k || ldc < n) {
+        set_error("mcq_gemm_nt: bad shape m=%lld n=%d k=%d lda=%lld ldb=%lld ldc=%lld", (long long)m, n, k, (long long)lda,
+                  (long long)ldb, (long long)ldc);
+        return MCQ_EINVAL;
+    }
+    if (n % 64 != 0 || (ldc & 3) || ((uintptr_t)out & 15)) {
+        set_error("mcq_gemm_nt: n=%d must be a multiple of 64, ldc=%lld a multiple of 4, out 16-byte aligned", n,
+                  (long long)ldc);
+        return MCQ_EUNSUPPORTED;
+    }
+    if (!a || !b || !out || !workspace) {
+        set_error("mcq_gemm_nt: null pointer");
+        return MCQ_EINVAL;
+    }
+    const NtPlan p = nt_plan(m, n, k);
+    if (workspace_bytes < p.bytes) {
+        set_error("mcq_gemm_nt: workspace of %zu bytes, need %zu", workspace_bytes, p.bytes);
+        return MCQ_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    int rc;
+    if ((rc = launch_pack_rows(a, m, k, lda, (__half *)(ws + p.off_pa), (float *)(ws + p.off_sa), p.Mp, p.Kp, st))) return rc;
+    if ((rc = launch_pack_rows(b, n, k, ldb, (__half *)(ws + p.off_pb), (float *)(ws + p.off_sb), p.Np, p.Kp, st))) return rc;
+    return launch_gemm_tc_general((const __half *)(ws + p.off_pa), (const float *)(ws + p.off_sa),
+                                  (const __half *)(ws + p.off_pb), (const float *)(ws + p.off_sb), out, ldc, m, p.Mp, n,
+                                  p.Kp, accumulate, st);
 }
 
 }  // extern "C"

@@ -11,8 +11,9 @@ Same constructor arguments, parameter names (`linear1`, `codebook_embedding`, `l
   * the cross entropy (:79-82) is one kernel (`mcq_jcl_cross_entropy`) that also leaves softmax - onehot in place of the
     logits, so the backward pass starts from it with no log-softmax graph;
   * the backward of the gather/cumsum/ReLU stage is one kernel (`mcq_jcl_hidden_backward`);
-  * the weight gradients (reductions over all frames) are split-K tcgen05 products (`mcq_gemm_tn`, fp32-faithful fp16x2
-    split); the remaining dense products are plain fp32 library GEMMs (cuBLAS through torch.mm / torch.bmm).
+  * the dense products -- fp32 SGEMMs in the reference -- are fp32-faithful tcgen05 products (fp16x2 operand split, fp32
+    accumulation): `mcq_gemm_nt` for the forward and input-gradient products, split-K `mcq_gemm_tn` for the weight
+    gradients (reductions over all frames).  Shapes whose widths are not multiples of 64 use the library GEMM.
 
 `checkpoint=True` keeps the reference's meaning (prediction.py:113-115: recompute in backward, store only the inputs).
 The codes may be the uint8 tensor `Quantizer.encode` returns (no int64 copy is made), int32 or int64 (negative =
@@ -24,6 +25,12 @@ from torch import Tensor, nn
 from . import _lib
 
 
+def _use_tc(B: int, P: int, H: int, K: int) -> bool:
+    """The tcgen05 products take output widths that are multiples of 64 (mcq_gemm_nt); tiny or odd shapes go to the
+    library GEMM (identical mathematics, fp32)."""
+    return B >= 256 and P % 64 == 0 and H % 64 == 0 and K % 64 == 0
+
+
 def _stages_forward(pred: Tensor, codes: Tensor, w1: Tensor, b1, emb: Tensor, w2: Tensor, w2b: Tensor, bias2: Tensor,
                     ignore_index: int, want_grad: bool):
     """Returns (row_loss (B, N), sums (2,), act (N, B, H), dlogits (B, N*K) or None)."""
@@ -32,16 +39,27 @@ def _stages_forward(pred: Tensor, codes: Tensor, w1: Tensor, b1, emb: Tensor, w2
     N, K, H = w2.shape
     dev = pred.device
     stream = _lib.stream_ptr(dev)
-    hidden = torch.addmm(b1, pred, w1.t()) if b1 is not None else pred.mm(w1.t())  # (B, H)  prediction.py:56
+    tc = _use_tc(B, P, H, K)
+    if tc:  # prediction.py:56 as an fp32-faithful tcgen05 product
+        hidden = _lib.gemm_nt(pred, w1)
+        if b1 is not None:
+            hidden.add_(b1)
+    else:
+        hidden = torch.addmm(b1, pred, w1.t()) if b1 is not None else pred.mm(w1.t())  # (B, H)
     act = torch.empty(N, B, H, dtype=torch.float32, device=dev)
     scale = 0.5 * ((H / N) ** 0.5)  # prediction.py:51
     with torch.cuda.device(dev):
         _lib.check(L.mcq_jcl_hidden_forward(hidden.data_ptr(), codes.data_ptr(), _lib.idx_dtype_code(codes), B, N, K, H,
                                             emb.data_ptr(), scale, act.data_ptr(), stream), "mcq_jcl_hidden_forward")
     # logits (B, N, K): predictor part as ONE product against all codebooks (:74-76), hidden part per codebook (:70-72)
-    logits = pred.mm(w2b.reshape(N * K, P).t())
-    lv = logits.view(B, N, K).transpose(0, 1)  # (N, B, K) view
-    lv.baddbmm_(act, w2.transpose(1, 2))
+    if tc:
+        logits = _lib.gemm_nt(pred, w2b.reshape(N * K, P))
+        for n in range(N):
+            _lib.gemm_nt(act[n], w2[n], out=logits[:, n * K:(n + 1) * K], accumulate=True)
+    else:
+        logits = pred.mm(w2b.reshape(N * K, P).t())
+        lv = logits.view(B, N, K).transpose(0, 1)  # (N, B, K) view
+        lv.baddbmm_(act, w2.transpose(1, 2))
     row_loss = torch.empty(B, N, dtype=torch.float32, device=dev)
     sums = torch.empty(2, dtype=torch.float32, device=dev)
     partials = torch.empty(L.mcq_jcl_partials(), dtype=torch.float32, device=dev)
@@ -91,7 +109,14 @@ class _JointCodebookLossFn(torch.autograd.Function):
         else:
             gs = g.to(torch.float32) if reduction == "sum" else g.to(torch.float32) / sums[1]
         dlv = dl.view(B, N, K).transpose(0, 1)  # (N, B, K) view
-        grad_act = torch.bmm(dlv, w2)  # (N, B, H)
+        tc = _use_tc(B, P, H, K)
+        if tc:
+            grad_act = torch.empty(N, B, H, dtype=torch.float32, device=dev)
+            w2t = w2.transpose(1, 2).contiguous()  # (N, H, K)
+            for n in range(N):
+                _lib.gemm_nt(dl[:, n * K:(n + 1) * K], w2t[n], out=grad_act[n])
+        else:
+            grad_act = torch.bmm(dlv, w2)  # (N, B, H)
         grad_hidden = torch.empty(B, H, dtype=torch.float32, device=dev)
         grad_emb = torch.zeros_like(emb)
         scale = 0.5 * ((H / N) ** 0.5)
@@ -103,8 +128,12 @@ class _JointCodebookLossFn(torch.autograd.Function):
         grad_w2 = torch.stack([_lib.gemm_tn(dl[:, n * K:(n + 1) * K], act[n]) for n in range(N)])  # (N, K, H)
         grad_w2b = _lib.gemm_tn(dl, pred).view(N, K, P)
         grad_bias2 = dl.sum(dim=0).view(N, K)
-        grad_pred = dl.mm(w2b.reshape(N * K, P))
-        grad_pred.addmm_(grad_hidden, w1)
+        if tc:
+            grad_pred = _lib.gemm_nt(dl, w2b.reshape(N * K, P).t().contiguous())
+            _lib.gemm_nt(grad_hidden, w1.t().contiguous(), out=grad_pred, accumulate=True)
+        else:
+            grad_pred = dl.mm(w2b.reshape(N * K, P))
+            grad_pred.addmm_(grad_hidden, w1)
         grad_w1 = _lib.gemm_tn(grad_hidden, pred)
         grad_b1 = grad_hidden.sum(dim=0) if has_b1 else None
         if gs is not None:  # everything above is linear in dl: scale the (small) results instead of the (B, N*K) tensor

@@ -98,13 +98,17 @@ def test_jcl_cross_entropy_stage():
     assert (dl.double() - ref_dl).abs().max().item() <= 2e-6
 
 
-def _torch_reference_loss(x, codes, mod):
-    """prediction.py:9-82 restated with PyTorch ops (fp32, the device's library kernels)."""
+def _torch_reference_loss(x, codes, mod, mask=None, return_pre=False):
+    """prediction.py:9-82 restated with PyTorch ops (fp32, the device's library kernels).  With `mask` (B, N, H) the ReLU
+    is applied as a product by that 0/1 mask (see the test below)."""
     N, K, H = mod.linear2_weight.shape
     c = codes.to(torch.int64)
     first = c[:, :-1].clamp(min=0) + torch.arange(0, (N - 1) * K, K, device=x.device)
     e = torch.nn.functional.embedding(first, mod.codebook_embedding.weight) * jo.embedding_scale(H, N)
-    a = torch.relu(torch.cumsum(torch.cat((mod.linear1(x).unsqueeze(1), e), dim=1), dim=1))
+    pre = torch.cumsum(torch.cat((mod.linear1(x).unsqueeze(1), e), dim=1), dim=1)
+    if return_pre:
+        return pre
+    a = torch.relu(pre) if mask is None else pre * mask
     lg = torch.matmul(a.transpose(0, 1), mod.linear2_weight.transpose(1, 2)).transpose(0, 1)
     lg = lg + torch.matmul(x, mod.linear2b_weight.transpose(1, 2)).transpose(0, 1) + mod.linear2_bias
     return torch.nn.functional.cross_entropy(lg.reshape(-1, K), c.reshape(-1), ignore_index=mod.ignore_index,
@@ -113,9 +117,14 @@ def _torch_reference_loss(x, codes, mod):
 
 @pytest.mark.parametrize("checkpoint", [False, True])
 def test_jcl_realistic_size_against_torch(checkpoint):
-    """8 codebooks of 256 predicted from 512 channels, 8,192 frames, codes straight from Quantizer.encode (uint8)."""
-    from quantization_b200 import JointCodebookLoss
-    from quantization_b200 import synth
+    """8 codebooks of 256 predicted from 512 channels, 8,192 frames, codes straight from Quantizer.encode (uint8); every
+    dense product on tcgen05 (mcq_gemm_nt / mcq_gemm_tn).
+
+    The function has 33 M ReLUs; two fp32 evaluations of linear1 differ in the last bits, so a handful of units whose
+    pre-activation is within rounding of zero switch side, and each switch moves a few gradient entries by a finite
+    amount.  That is adjudicated separately (few, and only at |pre-activation| < 1e-4); the gradients are then compared
+    with the PyTorch evaluation using OUR ReLU pattern, which makes the comparison smooth."""
+    from quantization_b200 import JointCodebookLoss, prediction, synth
     torch.manual_seed(3)
     P, N, K, H, B = 512, 8, 256, 512, 8192
     q = helpers.make_quantizer(256, N, K, synth.synth_params(256, N, K, 1), DEV)
@@ -129,7 +138,17 @@ def test_jcl_realistic_size_against_torch(checkpoint):
     gx = x.grad.clone()
     mod.zero_grad()
     x.grad = None
-    ref = _torch_reference_loss(x, codes, mod)
+    with torch.no_grad():
+        _, _, act, _ = prediction._stages_forward(x.detach(), codes, mod.linear1.weight, mod.linear1.bias,
+                                                  mod.codebook_embedding.weight, mod.linear2_weight, mod.linear2b_weight,
+                                                  mod.linear2_bias, -100, False)
+        ours_on = act.transpose(0, 1) > 0  # (B, N, H)
+        pre = _torch_reference_loss(x, codes, mod, return_pre=True)
+        switched = ours_on != (pre > 0)
+        assert switched.sum().item() <= 1e-5 * switched.numel()
+        if switched.any():
+            assert pre[switched].abs().max().item() <= 1e-4
+    ref = _torch_reference_loss(x, codes, mod, mask=ours_on.float())
     ref.backward()
     assert torch.allclose(loss, ref, rtol=1e-5)
     for n, p in mod.named_parameters():

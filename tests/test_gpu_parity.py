@@ -617,3 +617,28 @@ def test_gemm_tn_split_k(R, C1, C2, dt):
     _record("gemm_tn", f"{R}x{C1}x{C2}", {"worst_err_over_sum_abs": worst, "log2": float(np.log2(worst + 1e-300)),
                                          "library_sgemm_log2": float(np.log2(sgemm + 1e-300))})
     assert worst <= 2.0 ** -18, np.log2(worst)
+
+
+@pytest.mark.parametrize("M,N,K", [(5000, 256, 512), (300, 64, 100), (32768, 2048, 512), (1000, 512, 2048)])
+def test_gemm_nt(M, N, K):
+    """mcq_gemm_nt (a . b^T, per-row scaled fp16x2 split on tcgen05) against fp64, with rows of very different
+    magnitude, strided operands, a column-block destination and accumulation; error bound 2^-20 of sum |a b| per output
+    (the accuracy of the encode path's products), the library SGEMM's error recorded beside it."""
+    gen = torch.Generator().manual_seed(M + N)
+    a = (torch.randn(M, K + 8, generator=gen) * torch.exp(3 * torch.randn(M, 1, generator=gen))).to(DEV)[:, 4:4 + K]
+    b = (torch.randn(N, K, generator=gen) * torch.exp(2 * torch.randn(N, 1, generator=gen))).to(DEV)
+    wide = torch.randn(M, N + 128, generator=gen).to(DEV)
+    base = wide.clone()
+    dst = wide[:, 64:64 + N]
+    _lib.gemm_nt(a, b, out=dst, accumulate=True)
+    assert torch.equal(wide[:, :64], base[:, :64]) and torch.equal(wide[:, 64 + N:], base[:, 64 + N:])
+    a64, b64 = a.double(), b.double()
+    ref = a64.mm(b64.t())
+    mag = a64.abs().mm(b64.abs().t()) + base[:, 64:64 + N].double().abs() + 1e-300
+    worst = ((dst.double() - base[:, 64:64 + N].double() - ref).abs() / mag).max().item()
+    out = _lib.gemm_nt(a, b)
+    w2 = ((out.double() - ref).abs() / mag).max().item()
+    sgemm = ((a.mm(b.t()).double() - ref).abs() / mag).max().item()
+    _record("gemm_nt", f"{M}x{N}x{K}", {"log2_err": float(np.log2(w2 + 1e-300)), "log2_err_accumulate": float(np.log2(worst + 1e-300)),
+                                        "library_sgemm_log2": float(np.log2(sgemm + 1e-300))})
+    assert w2 <= 2.0 ** -20 and worst <= 2.0 ** -20, (np.log2(w2), np.log2(worst))
