@@ -121,6 +121,22 @@ int mcq_class_loss_backward(const float *xw, int64_t num_frames, int dim, int nu
                             const float *g_prob_sum, float *grad_logits, float *part_gx, void *stream);
 
 /*
+ * Reconstruction term of Quantizer.compute_loss (quantization.py:209-216) without its (B, dim) intermediates.
+ * Forward: sums[0] = sum_{b,d} (x_hat - x)^2 with x_hat = decode(idx) (scaled centers summed n = 0..N-1), sums[1] =
+ * sum_{b,d} (x - mean)^2 (mean (dim) fp32 = Quantizer.get_data_mean()); x (B, dim) fp32 / fp16 / bf16, idx (B, N) int64;
+ * partials: mcq_recon_loss_partials() floats of scratch; fixed-order sums (reproducible).
+ * Backward: grad_scaled_centers (N, K, dim) += coef[0] * (x_hat - x) scattered to the chosen centers (coef: DEVICE
+ * scalar, = 2 * upstream gradient of sums[0]; zero the gradient first).  dim <= 1024.
+ */
+int mcq_recon_loss_partials(void);
+int mcq_recon_loss_forward(const void *x, int x_dtype, const int64_t *idx, int64_t num_frames, int num_codebooks,
+                           int codebook_size, int dim, const float *scaled_centers, const float *mean, float *sums,
+                           float *partials, void *stream);
+int mcq_recon_loss_backward(const void *x, int x_dtype, const int64_t *idx, int64_t num_frames, int num_codebooks,
+                            int codebook_size, int dim, const float *scaled_centers, const float *coef,
+                            float *grad_scaled_centers, void *stream);
+
+/*
  * Weight-gradient product: out (c1, c2) = a^T . b, reduction over `rows` frames; a (rows, c1) fp32 with row stride lda,
  * b (rows, c2) fp32 / fp16 / bf16 with row stride ldb (elements).  This is what the reference's autograd computes with
  * an fp32 SGEMM for d loss / d to_logits.weight (backward of quantization.py:279) and for the linear1 / linear2 /

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libmcq.so")
-SOURCES = ["api.cu", "prepare.cu", "gemm_ffma.cu", "gemm_tc.cu", "gemm_tn.cu", "search.cu", "search2.cu", "search_k16.cu", "decode.cu", "loss.cu", "jcl.cu", "host.cu"]
+SOURCES = ["api.cu", "prepare.cu", "gemm_ffma.cu", "gemm_tc.cu", "gemm_tn.cu", "search.cu", "search2.cu", "search_k16.cu", "decode.cu", "loss.cu", "recon.cu", "jcl.cu", "host.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]

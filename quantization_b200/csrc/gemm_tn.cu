@@ -32,14 +32,16 @@ template <typename T>
 __global__ void __launch_bounds__(256) absmax_kernel(const T *__restrict__ x, int64_t rows, int cols, int64_t ld,
                                                      unsigned *__restrict__ out) {
     float m = 0.0f;
-    const int64_t n = rows * cols;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / cols;
-        m = fmaxf(m, fabsf(to_f32(x[r * ld + (i - r * cols)])));
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = warp; r < rows; r += nwarps) {  // a warp per row: coalesced, no 64-bit divisions
+        const T *row = x + r * ld;
+        for (int c = lane; c < cols; c += 32) m = fmaxf(m, fabsf(to_f32(row[c])));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out, __float_as_uint(m));
+    if (lane == 0 && m > 0.0f) atomicMax(out, __float_as_uint(m));
 }
 
 // power of two that brings the largest magnitude into [2^13, 2^14) (fp16 pieces then never overflow)
@@ -209,7 +211,7 @@ TnPlan tn_plan(int64_t R, int C1, int C2) {
 template <typename T>
 int pack_operand(const T *X, int64_t R, int C, int64_t ld, unsigned *absmax, __half *planes, int64_t Rp, int Cp,
                  float *inv_scale, int n_scale, cudaStream_t st) {
-    int64_t blocks = (R * C + 255) / 256;
+    int64_t blocks = (R + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
     absmax_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(X, R, C, ld, absmax);
     MCQ_LAUNCH_CHECK("absmax_kernel");

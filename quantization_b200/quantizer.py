@@ -55,6 +55,43 @@ class _DecodeFn(torch.autograd.Function):
         return grad, None
 
 
+class _ReconLossFn(torch.autograd.Function):
+    """(sum (x_hat - x)^2, sum (x - mean)^2) with x_hat = decode(indexes), differentiable in the scaled centers
+    (reference: quantization.py:209-216).  One kernel forward (`mcq_recon_loss_forward`: no x_hat, no difference, no
+    squares in memory), one kernel backward (`mcq_recon_loss_backward`: recomputes x_hat - x and scatter-adds)."""
+
+    @staticmethod
+    def forward(ctx, scaled_centers: Tensor, indexes: Tensor, x: Tensor, mean: Tensor) -> Tensor:
+        N, K, D = scaled_centers.shape
+        B = indexes.shape[0]
+        L = _lib.lib()
+        cs = scaled_centers.detach().contiguous()
+        sums = torch.empty(2, dtype=torch.float32, device=cs.device)
+        partials = torch.empty(L.mcq_recon_loss_partials(), dtype=torch.float32, device=cs.device)
+        mean = mean.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(cs.device):
+            rc = L.mcq_recon_loss_forward(x.data_ptr(), _lib.x_dtype_code(x), indexes.data_ptr(), B, N, K, D,
+                                          cs.data_ptr(), mean.data_ptr(), sums.data_ptr(), partials.data_ptr(),
+                                          _lib.stream_ptr(cs.device))
+        _lib.check(rc, "mcq_recon_loss_forward")
+        ctx.save_for_backward(cs, indexes, x)
+        ctx.mark_non_differentiable(indexes)
+        return sums
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        cs, indexes, x = ctx.saved_tensors
+        N, K, D = cs.shape
+        L = _lib.lib()
+        coef = (2.0 * g[0]).to(torch.float32).reshape(1).contiguous()  # d sums[0] / d x_hat = 2 (x_hat - x); sums[1]: no grad
+        grad = torch.zeros(N, K, D, dtype=torch.float32, device=cs.device)
+        with torch.cuda.device(cs.device):
+            rc = L.mcq_recon_loss_backward(x.data_ptr(), _lib.x_dtype_code(x), indexes.data_ptr(), indexes.shape[0], N, K,
+                                           D, cs.data_ptr(), coef.data_ptr(), grad.data_ptr(), _lib.stream_ptr(cs.device))
+        _lib.check(rc, "mcq_recon_loss_backward")
+        return grad, None, None, None
+
+
 class _ClassLossFn(torch.autograd.Function):
     """(logprob_sum, prob_sum) of the classifier logits as a differentiable function of the classifier parameters
     (reference: `_logits` -> log_softmax -> gather / exp -> mean, quantization.py:220-235).  The forward GEMM and the
@@ -331,20 +368,26 @@ class Quantizer(nn.Module):
         x = x.reshape(-1, self.dim)
         with torch.no_grad():
             indexes = self._compute_indexes(x, refine_indexes_iters)
-        xf = x.float() if x.dtype != torch.float32 else x
-        needs_grad = torch.is_grad_enabled() and (self.centers.requires_grad or self.centers_scale.requires_grad)
-        if needs_grad:
-            x_approx = _DecodeFn.apply(self.get_centers(), indexes)
+        if self.dim <= 1024 and x.shape[0] > 0:
+            # :209-216 fused: both sums from one pass over the frames, gradient w.r.t. the scaled centers from another
+            sums = _ReconLossFn.apply(self.get_centers(), indexes, self._check_x(x), self.get_data_mean())
+            rel_reconstruction_loss = sums[0] / (sums[1] + 1.0e-20)
         else:
-            x_approx = self.decode(indexes)
-        tot_error = x_approx - xf
-        rel_reconstruction_loss = (tot_error ** 2).sum() / (((xf - self.get_data_mean()) ** 2).sum() + 1.0e-20)
+            xf = x.float() if x.dtype != torch.float32 else x
+            needs_grad = torch.is_grad_enabled() and (self.centers.requires_grad or self.centers_scale.requires_grad)
+            if needs_grad:
+                x_approx = _DecodeFn.apply(self.get_centers(), indexes)
+            else:
+                x_approx = self.decode(indexes)
+            tot_error = x_approx - xf
+            rel_reconstruction_loss = (tot_error ** 2).sum() / (((xf - self.get_data_mean()) ** 2).sum() + 1.0e-20)
 
         N, K = self.num_codebooks, self.codebook_size
-        B = xf.shape[0]
+        B = x.shape[0]
         if B == 0 or K > 256 or K < 32:
             # K < 32 (trainer phase 1, K = 16): the (B, N*K) logits are small and the PyTorch formulation is the
             # faster one (measured at B = 65,536: 3.1 vs 3.5 ms per step)
+            xf = x.float() if x.dtype != torch.float32 else x
             return self._compute_loss_tail_torch(xf, indexes, rel_reconstruction_loss)
         # logprob / entropy terms (reference :218-240) from two fused reductions over the logits
         xc = self._check_x(x)

@@ -83,6 +83,34 @@ int main(int argc, char **argv) {
         cudaMemcpy(&lp, d_lp, 4, cudaMemcpyDeviceToHost);
         printf("logprob_sum %.6f\n", lp);
     }
+    if (D <= 1024) {  // fused reconstruction loss, forward and backward; weight-gradient and general products
+        float *d_sums, *d_rp, *d_coef, *d_mean;
+        cudaMalloc(&d_sums, 8); cudaMalloc(&d_rp, (size_t)mcq_recon_loss_partials() * 4); cudaMalloc(&d_coef, 4);
+        cudaMalloc(&d_mean, D * 4);
+        cudaMemset(d_mean, 0, D * 4);
+        float two = 2.0f;
+        cudaMemcpy(d_coef, &two, 4, cudaMemcpyHostToDevice);
+        const float *cs = mcq_prepared_scaled_centers(blob, N, K, D);
+        CK(mcq_recon_loss_forward(d_x, xdt == 0 ? MCQ_F32 : MCQ_F16, d_idx2, B, N, K, D, cs, d_mean, d_sums, d_rp, nullptr));
+        cudaMemset(d_grad, 0, NK * D * 4);
+        CK(mcq_recon_loss_backward(d_x, xdt == 0 ? MCQ_F32 : MCQ_F16, d_idx2, B, N, K, D, cs, d_coef, d_grad, nullptr));
+        float sums[2] = {0, 0};
+        cudaMemcpy(sums, d_sums, 8, cudaMemcpyDeviceToHost);
+        printf("recon sums %.4f %.4f\n", sums[0], sums[1]);
+        // out (D, D) = d_out^T . d_out over the B frames, and out2 (B, 64k) = d_out . cs[:n]^T
+        const size_t wtn = mcq_gemm_tn_workspace_bytes(B, D, D);
+        void *d_wtn; float *d_tn;
+        cudaMalloc(&d_wtn, wtn); cudaMalloc(&d_tn, (size_t)D * D * 4);
+        CK(mcq_gemm_tn(d_out, D, d_out, MCQ_F32, D, B, D, D, d_tn, d_wtn, wtn, nullptr));
+        const int nn = (int)(NK / 64 * 64) > 256 ? 256 : (int)(NK / 64 * 64);
+        if (nn >= 64) {
+            const size_t wnt = mcq_gemm_nt_workspace_bytes(B, nn, D);
+            void *d_wnt; float *d_nt;
+            cudaMalloc(&d_wnt, wnt); cudaMalloc(&d_nt, (size_t)B * nn * 4);
+            CK(mcq_gemm_nt(d_out, D, cs, D, B, nn, D, d_nt, nn, 0, d_wnt, wnt, nullptr));
+            CK(mcq_gemm_nt(d_out, D, cs, D, B, nn, D, d_nt, nn, 1, d_wnt, wnt, nullptr));
+        }
+    }
     cudaError_t e = cudaDeviceSynchronize();
     std::vector<unsigned char> codes((size_t)B * cols);
     cudaMemcpy(codes.data(), d_codes, codes.size(), cudaMemcpyDeviceToHost);
