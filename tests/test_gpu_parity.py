@@ -642,3 +642,43 @@ def test_gemm_nt(M, N, K):
     _record("gemm_nt", f"{M}x{N}x{K}", {"log2_err": float(np.log2(w2 + 1e-300)), "log2_err_accumulate": float(np.log2(worst + 1e-300)),
                                         "library_sgemm_log2": float(np.log2(sgemm + 1e-300))})
     assert w2 <= 2.0 ** -20 and worst <= 2.0 ** -20, (np.log2(w2), np.log2(worst))
+
+
+def test_trainer_cuda_graph_equals_eager():
+    """The CUDA-graph replay of a trainer step (trainer.py) against the same steps launched eagerly: same seeds, same
+    batches.  The scatter-adds use floating-point atomics, so the two runs agree to rounding, not bitwise -- and since
+    training on discrete codes amplifies rounding differences over many steps, the comparison is made over a dozen steps
+    (three eager warm-up steps, the capture, then replays), after every step."""
+    import random
+    from quantization_b200 import QuantizerTrainer
+    dim = 64
+    gen = torch.Generator().manual_seed(11)
+    batches = [torch.randn(2048, dim, generator=gen).to(DEV) for _ in range(4)]
+    trainers = []
+    for mode in ("0", "1"):
+        os.environ["MCQ_TRAINER_GRAPH"] = mode
+        try:
+            torch.manual_seed(5)
+            random.seed(5)
+            tr = QuantizerTrainer(dim=dim, bytes_per_frame=2, device=DEV, phase_one_iters=1000, phase_two_iters=1000)
+            assert tr._use_graph == (mode == "1")
+            tr.two_iter_prob = 0.0  # one configuration, so the capture happens at the fourth step
+            tr.cur_iter = 1
+            trainers.append(tr)
+        finally:
+            del os.environ["MCQ_TRAINER_GRAPH"]
+    eager, graphed = trainers
+    for i in range(12):
+        for tr in trainers:
+            tr.step(batches[i % len(batches)])
+        assert (len(graphed._graphs) > 0) == (i >= 3), i
+        for (k, a), (_, b) in zip(eager.quantizer.state_dict().items(), graphed.quantizer.state_dict().items()):
+            if a.dtype.is_floating_point:
+                assert (a - b).abs().max().item() <= 1e-4 * (a.abs().max().item() + 1e-6), (i, k)
+    # the phase switch drops the graphs and the product quantizer trains on
+    graphed.cur_iter = graphed.phase_one_iters
+    graphed.step(batches[0])
+    assert graphed.quantizer.codebook_size == 256 and not graphed._graphs
+    for i in range(6):
+        graphed.step(batches[i % len(batches)])
+    assert len(graphed._graphs) > 0
