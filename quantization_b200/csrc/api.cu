@@ -146,6 +146,9 @@ struct ProfScope {
     cudaEvent_t end = nullptr;
     ProfScope(int kind, cudaStream_t s) : st(s) {
         if (!g_prof.on) return;
+        // timing events cannot be recorded into a CUDA-graph capture (the trainer captures whole steps)
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return;
         std::lock_guard<std::mutex> lock(g_prof.mu);
         if (g_prof.used * 2 + 2 > g_prof.ev.size()) {
             cudaEvent_t a = nullptr, b = nullptr;

@@ -139,8 +139,12 @@ class QuantizerTrainer(object):
         self.cur_iter += 1
 
     def _init_optimizer(self):
+        # same hyper-parameters as the reference (:722-727).  On a GPU: the fused multi-tensor implementation (one
+        # kernel instead of ~12 foreach kernels of 10 us each; it is also the graph-capturable one)
+        on_gpu = next(self.quantizer.parameters()).is_cuda
         self.optim = torch.optim.Adam(self.quantizer.parameters(), lr=self.lr, betas=(0.9, 0.98), eps=1e-9,
-                                      weight_decay=1.0e-06, capturable=self._use_graph)
+                                      weight_decay=1.0e-06,
+                                      **({"fused": True, "capturable": self._use_graph} if on_gpu else {}))
         self._graphs.clear()
         self._warm.clear()
         step_size = (self.phase_one_iters if self.cur_iter == 0 else self.phase_two_iters) / 4

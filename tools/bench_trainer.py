@@ -2,7 +2,8 @@
 """QuantizerTrainer.step timing at BASELINE configs[2]: dim=256, bytes_per_frame=4, batch=65536 bf16.
     python tools/bench_trainer.py [steps_per_phase] [batch]
 Times `steps` steps in phase 1 (K=16, N=8) and in phase 2 (K=256, N=4) with CUDA events, and prints where a step's
-GPU time goes (library kernels by kind via mcq_profile, the rest = PyTorch loss/backward/Adam)."""
+GPU time goes (library kernels by kind via mcq_profile -- only meaningful with MCQ_TRAINER_GRAPH=0: launches replayed
+from a CUDA graph carry no timing events -- the rest = PyTorch loss arithmetic / Adam)."""
 import os
 import random
 import sys
@@ -24,7 +25,7 @@ x = synth.synth_x(B, D, 1234 + 2, torch.bfloat16).to(dev)
 
 
 def run(tr, tag):
-    for _ in range(3):
+    for _ in range(16):  # long enough for both refinement-pass counts to be captured (3 eager steps each, then the capture)
         tr.step(x)
     torch.cuda.synchronize()
     _lib.profile(True)
