@@ -58,55 +58,96 @@ def load_traffic():
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML in a thread (nvidia_ml_py: the same counters
+    `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints, every 20 ms, no process start-up
+    inside the window); if NVML cannot be loaded, an `nvidia-smi -lms 100` loop over the same window."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.f = None
         self.p = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.source = None
+
+    def _nvml_loop(self, nv, h):
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        while True:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            if self.stop_flag:
+                break
+            time.sleep(0.02)
 
     def start(self):
         try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.idx
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
                                        "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
+            self.source = "nvidia-smi"
         except Exception:
             self.p = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
-            c = [v.strip() for v in line.split(",")]
-            if len(c) < 9:
-                continue
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=5)
+        elif self.p is not None:
+            self.p.terminate()
             try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+            self.f.flush()
+            self.f.seek(0)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for line in self.f.read().splitlines():
+                c = [v.strip() for v in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    self.sm.append(float(c[1]))
+                    self.mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(names, c[5:9]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+            try:
+                os.unlink(self.f.name)
+            except OSError:
+                pass
+        if self.sm:
+            out = {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons),
+                   "samples": len(self.sm), "source": self.source}
         return out
 
 
