@@ -458,7 +458,7 @@ int mcq_class_loss_forward(const void *x, int x_dtype, int64_t B, int D, int N, 
         if (rc) return rc;
     }
     // partial sums live in the (now unused) P region of the workspace
-    const int ns = class_loss_streams(B, N);
+    const int ns = class_loss_streams(B, N, K);
     float *part_prob = (float *)(ws + W.off_p);
     const size_t need = sizeof(float) * ((size_t)ns * L.NK + (size_t)ns * N);
     if (need > sizeof(float) * (size_t)W.Mp * L.NK) {

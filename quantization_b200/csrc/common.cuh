@@ -109,7 +109,7 @@ int launch_decode(const void *codes, int codes_dtype, int64_t B, int ncols, int 
 int launch_decode_backward(const float *grad_out, const int64_t *idx, int64_t B, int N, int K, int D, float *grad,
                            cudaStream_t st);
 
-int class_loss_streams(int64_t B, int N);
+int class_loss_streams(int64_t B, int N, int K);
 int launch_class_loss_fwd(const float *xw, const float *bias, const int64_t *idx, int64_t B, int N, int K,
                           float *part_prob, float *part_lp, float *prob_sum, float *logprob_sum, cudaStream_t st);
 int class_loss_bwd_partials();

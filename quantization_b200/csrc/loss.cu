@@ -207,6 +207,125 @@ __global__ void __launch_bounds__(256) class_loss_bwd_kernel(const float *__rest
     if (lane == 0) part_gx[blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = gx;
 }
 
+// ---- small codebooks (K = 16 or 32: trainer phase 1): one THREAD per (frame stream, codebook) row.  A row is K*4
+// contiguous bytes, a warp reads 32 consecutive rows; no shuffles, the softmax lives in the thread's registers.  Same
+// partial-sum layout and frame assignment as the segment kernels above (thread gs: codebook gs % N, frames gs / N,
+// gs / N + nstreams, ...), just with many more streams. ----
+template <int K>
+__device__ __forceinline__ void row_softmax_thread(const float *__restrict__ xw, const float *__restrict__ bias,
+                                                   float (&s)[K], float (&raw)[K], float &m, float &lsum) {
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q) {
+        const float4 a = *reinterpret_cast<const float4 *>(xw + 4 * q);
+        const float4 c = __ldg(reinterpret_cast<const float4 *>(bias) + q);
+        raw[4 * q] = a.x;
+        raw[4 * q + 1] = a.y;
+        raw[4 * q + 2] = a.z;
+        raw[4 * q + 3] = a.w;
+        s[4 * q] = a.x + c.x;
+        s[4 * q + 1] = a.y + c.y;
+        s[4 * q + 2] = a.z + c.z;
+        s[4 * q + 3] = a.w + c.w;
+    }
+    m = s[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) m = fmaxf(m, s[k]);
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        s[k] = s[k] - m;      // shifted logits; turned into probabilities by the caller
+        sum += expf(s[k]);
+    }
+    lsum = logf(sum);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) class_loss_fwd_small_kernel(const float *__restrict__ xw, const float *__restrict__ bias,
+                                                                   const int64_t *__restrict__ idx, int64_t B, int N,
+                                                                   int nstreams, float *__restrict__ part_prob,
+                                                                   float *__restrict__ part_lp) {
+    const int64_t gs = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = gs < (int64_t)nstreams * N;
+    const int n = (int)(gs % N);
+    const int64_t st = gs / N;
+    const size_t NK = (size_t)N * K;
+    float acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.0f;
+    float lp = 0.0f;
+    for (int64_t b = live ? st : B; b < B; b += nstreams) {
+        float s[K], raw[K], m, lsum;
+        row_softmax_thread<K>(xw + (size_t)b * NK + (size_t)n * K, bias + (size_t)n * K, s, raw, m, lsum);
+        const int kc = (int)idx[(size_t)b * N + n];
+        const float inv = expf(-lsum);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            acc[k] += expf(s[k]) * inv;
+            if (k == kc) lp += s[k] - lsum;
+        }
+    }
+    // block-level sum in a fixed order (thread t: codebook t % N, frame slot t / N; 256 % N == 0): one partial row
+    // per BLOCK, so the final pass over the partial rows stays short
+    __shared__ float red[256][K + 1];
+    __shared__ float redlp[256];
+#pragma unroll
+    for (int k = 0; k < K; ++k) red[threadIdx.x][k] = acc[k];
+    redlp[threadIdx.x] = lp;
+    __syncthreads();
+    const int slots = 256 / N;
+    for (int c = threadIdx.x; c < N * K; c += 256) {
+        const int cn = c / K, ck = c % K;
+        float t = 0.0f;
+        for (int f = 0; f < slots; ++f) t += red[f * N + cn][ck];
+        part_prob[(size_t)blockIdx.x * NK + c] = t;
+    }
+    if (threadIdx.x < N) {
+        float t = 0.0f;
+        for (int f = 0; f < slots; ++f) t += redlp[f * N + threadIdx.x];
+        part_lp[(size_t)blockIdx.x * N + threadIdx.x] = t;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) class_loss_bwd_small_kernel(const float *__restrict__ xw, const float *__restrict__ bias,
+                                                                   const int64_t *__restrict__ idx, int64_t B, int N,
+                                                                   const float *__restrict__ g_lp,
+                                                                   const float *__restrict__ g_prob,
+                                                                   float *__restrict__ grad_logits,
+                                                                   float *__restrict__ part_gx) {
+    const int64_t rows = B * N;
+    const float glp = *g_lp;
+    float gx = 0.0f;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(r % N);
+        float s[K], raw[K], m, lsum;
+        row_softmax_thread<K>(xw + (size_t)r * K, bias + (size_t)n * K, s, raw, m, lsum);
+        const int kc = (int)idx[r];
+        const float inv = expf(-lsum);
+        float dotc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            s[k] = expf(s[k]) * inv;
+            dotc += __ldg(g_prob + (size_t)n * K + k) * s[k];
+        }
+        float *g = grad_logits + (size_t)r * K;
+#pragma unroll
+        for (int q = 0; q < K / 4; ++q) {
+            float o[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int k = 4 * q + t;
+                o[t] = glp * ((k == kc ? 1.0f : 0.0f) - s[k]) + s[k] * (__ldg(g_prob + (size_t)n * K + k) - dotc);
+                gx += o[t] * raw[k];
+            }
+            *reinterpret_cast<float4 *>(g + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    // fixed work assignment + shuffle tree: the per-warp partials are reproducible
+    gx = seg_sum<32>(gx);
+    if ((threadIdx.x & 31) == 0) part_gx[blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = gx;
+}
+
 // K -> (segment width, elements per lane)
 #define MCQ_LOSS_DISPATCH(K, CALL)                 \
     switch (K) {                                   \
@@ -220,8 +339,9 @@ __global__ void __launch_bounds__(256) class_loss_bwd_kernel(const float *__rest
 }  // namespace
 
 // number of frame streams (and so of partial rows) the forward kernel uses for a batch of B frames
-int class_loss_streams(int64_t B, int N) {
+int class_loss_streams(int64_t B, int N, int K) {
     int64_t segs = (int64_t)148 * 4 * 8;  // 4 CTAs of 8 warps per SM
+    if (K == 16 || K == 32) segs = (int64_t)148 * 8 * 256 / 4;  // thread-per-row kernels: ~75 k threads
     int64_t st = segs / N;
     if (st > B / 2) st = B / 2;  // the partial rows live in a region of (B rounded up to 128) x N*K floats
     if (st < 1) st = 1;
@@ -234,7 +354,20 @@ int launch_class_loss_fwd(const float *xw, const float *bias, const int64_t *idx
         set_error("class loss: codebook_size %d > 256", K);
         return MCQ_EUNSUPPORTED;
     }
-    const int ns = class_loss_streams(B, N);
+    const int ns = class_loss_streams(B, N, K);
+    if ((K == 16 || K == 32) && 256 % N == 0) {
+        const int64_t threads = (int64_t)ns * N;
+        const unsigned blocks = (unsigned)((threads + 255) / 256);
+        if (K == 16)
+            class_loss_fwd_small_kernel<16><<<blocks, 256, 0, st>>>(xw, bias, idx, B, N, ns, part_prob, part_lp);
+        else
+            class_loss_fwd_small_kernel<32><<<blocks, 256, 0, st>>>(xw, bias, idx, B, N, ns, part_prob, part_lp);
+        MCQ_LAUNCH_CHECK("class_loss_fwd_small_kernel");
+        class_loss_reduce_kernel<<<(N * K + 31) / 32, 1024, 0, st>>>(part_prob, part_lp, (int)blocks, N, K, prob_sum,
+                                                                     logprob_sum);
+        MCQ_LAUNCH_CHECK("class_loss_reduce_kernel");
+        return MCQ_OK;
+    }
     const int spw = K >= 32 ? 1 : 2;
     const int warps = (ns * N + spw - 1) / spw;
     const int blocks = (warps + 7) / 8;
@@ -261,6 +394,16 @@ int launch_class_loss_bwd(const float *xw, const float *bias, const int64_t *idx
     int64_t blocks = (B * N + 8 * spw - 1) / (8 * spw);
     if (blocks > 148 * 8) blocks = 148 * 8;
     MCQ_CUDA(cudaMemsetAsync(part_gx, 0, sizeof(float) * class_loss_bwd_partials(), st));  // unused warps stay 0
+    if ((K == 16 || K == 32) && 256 % N == 0) {
+        int64_t nb = (B * N + 255) / 256;
+        if (nb > 148 * 8) nb = 148 * 8;
+        if (K == 16)
+            class_loss_bwd_small_kernel<16><<<(unsigned)nb, 256, 0, st>>>(xw, bias, idx, B, N, g_lp, g_prob, grad_logits, part_gx);
+        else
+            class_loss_bwd_small_kernel<32><<<(unsigned)nb, 256, 0, st>>>(xw, bias, idx, B, N, g_lp, g_prob, grad_logits, part_gx);
+        MCQ_LAUNCH_CHECK("class_loss_bwd_small_kernel");
+        return MCQ_OK;
+    }
 #define MCQ_BWD(W, EPL)                                                                                              \
     class_loss_bwd_kernel<W, EPL><<<(unsigned)blocks, 256, 0, st>>>(xw, bias, idx, B, N, K, g_lp, g_prob, grad_logits, \
                                                                     part_gx)
