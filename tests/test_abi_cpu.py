@@ -112,3 +112,28 @@ def test_trainer_construction_matches_reference_settings():
     assert not tr.done()
     with pytest.raises(AssertionError):
         QuantizerTrainer(dim=16, bytes_per_frame=3, device=torch.device("cpu"))
+
+
+def test_joint_codebook_loss_mirror_has_the_reference_parameters():
+    """quantization_b200.JointCodebookLoss keeps the reference module's parameter names, shapes and construction
+    (prediction.py:128-152): the state_dict of the reference-generated fixture loads unchanged.  (No compute: there is no
+    CPU path; a CPU tensor is rejected loudly.)"""
+    import numpy as np
+    import pytest
+    import torch
+    import helpers
+    from quantization_b200 import JointCodebookLoss
+    g, meta = helpers.jcl_golden()
+    for name in helpers.jcl_case_names():
+        m, pred, codes, par, _ = helpers.jcl_case(g, meta, name)
+        mod = JointCodebookLoss(m["P"], m["N"], hidden_channels=m["H"], codebook_size=m["K"], reduction=m["reduction"])
+        sd = mod.state_dict()
+        assert set(sd.keys()) == set(par.keys())
+        for k, v in par.items():
+            assert tuple(sd[k].shape) == v.shape, k
+        mod.load_state_dict({k: torch.from_numpy(v) for k, v in par.items()})
+        assert np.array_equal(mod.linear2_weight.detach().numpy(), par["linear2_weight"])
+    with pytest.raises(RuntimeError):
+        mod(torch.from_numpy(pred), torch.from_numpy(codes))
+    with pytest.raises(AssertionError):
+        JointCodebookLoss(8, 1)  # num_codebooks must be > 1 (prediction.py:128)
