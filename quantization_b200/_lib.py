@@ -151,11 +151,6 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def gemm_nt_supported(a: torch.Tensor, b: torch.Tensor) -> bool:
-    """Shapes the tcgen05 product takes (others go to a library GEMM in the host layer)."""
-    return b.shape[0] % 64 == 0 and a.shape[0] >= 256
-
-
 def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor = None, accumulate: bool = False) -> torch.Tensor:
     """a . b^T on the tensor cores (include/mcq.h: mcq_gemm_nt): a (M, K), b (N, K) fp32 with unit inner stride (row
     slices / column blocks of wider matrices are fine) -> out (M, N) fp32, which may itself be a column block."""

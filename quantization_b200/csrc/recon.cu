@@ -9,6 +9,8 @@
 //             (Measured and dropped: a private copy of the gradient per CTA in shared memory for small tables -- float
 //             atomics on shared memory compile to compare-and-swap loops, 177 us against 130 us for global atomics
 //             at 65,536 frames, N*K = 128.)
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mcq {
@@ -267,6 +269,80 @@ __global__ void __launch_bounds__(256) recon_bwd4_kernel(const T *__restrict__ x
     }
 }
 
+// ---- backward for small tables (codebook_size 16: trainer phase 1).  65,536 frames scatter into 128 rows, so atomics --
+// global or shared -- serialise on a few addresses (149 us, ncu: issue 16 %).  Here the sums are formed in REGISTERS:
+// a CTA stages coef * (x_hat - x) of 32 frames in shared memory; warp (n, h) owns codebook n and the h-th 128 columns,
+// keeps the 16 rows of that codebook as 16 float4 accumulators per lane and adds each staged frame into the one its
+// (warp-uniform) code selects; one round of vector atomics per CTA at the end.  Measured 119 us at 65,536 frames x 8
+// codebooks (the atomic kernel: 142-149 us); what remains is the latency of staging a tile (16 warps per SM at 128
+// registers, two barriers per 32 frames) -- double-buffering the tile is the next step. ----
+template <typename T, int VC>
+__global__ void __launch_bounds__(512, 1) recon_bwd_k16_kernel(const T *__restrict__ x, const int64_t *__restrict__ idx,
+                                                               int64_t B, int N, int D, const float *__restrict__ cs,
+                                                               const float *__restrict__ coef, float *__restrict__ grad) {
+    constexpr int K = 16, F = 32;
+    extern __shared__ float4 tile[];              // [F][D / 4]
+    __shared__ int rows_s[F][64];                 // n * K + code, per staged frame
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;           // == N * VC
+    const int my_n = warp / VC, my_h = warp % VC;
+    const int D4 = D >> 2;
+    const float cf = __ldg(coef);
+    float4 a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15;
+    a0 = a1 = a2 = a3 = a4 = a5 = a6 = a7 = a8 = a9 = a10 = a11 = a12 = a13 = a14 = a15 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t b0 = (int64_t)blockIdx.x * F; b0 < B; b0 += (int64_t)gridDim.x * F) {
+        // codes of the whole tile in one coalesced pass (takes a dependent global round trip out of every frame)
+        for (int i = threadIdx.x; i < F * N; i += blockDim.x) {
+            const int f = i / N, n = i - f * N;
+            const int64_t b = b0 + f;
+            int r = -1;
+            if (b < B) {
+                long long k = idx[(size_t)b * N + n];
+                k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+                r = n * K + (int)k;
+            }
+            rows_s[f][n] = r;
+        }
+        __syncthreads();
+        // stage: warp w computes frames w, w + nwarps, ... of this tile
+        for (int f = warp; f < F; f += nwarps) {
+            const int64_t b = b0 + f;
+            if (b < B) {
+                float4 e[VC], xv[VC];
+                frame_error4<T, VC>(x + (size_t)b * D, cs, rows_s[f], N, D, lane, e, xv);
+#pragma unroll
+                for (int c = 0; c < VC; ++c)
+                    tile[f * D4 + c * 32 + lane] = make_float4(cf * e[c].x, cf * e[c].y, cf * e[c].z, cf * e[c].w);
+            }
+        }
+        __syncthreads();
+        // accumulate: my codebook, my 128 columns
+        if (my_n < N) {
+#pragma unroll 4
+            for (int f = 0; f < F; ++f) {
+                const int r = rows_s[f][my_n];
+                if (r < 0) continue;
+                const float4 v = tile[f * D4 + my_h * 32 + lane];
+#define MCQ_ACC(i) case i: a##i.x += v.x; a##i.y += v.y; a##i.z += v.z; a##i.w += v.w; break;
+                switch (r - my_n * K) {
+                    MCQ_ACC(0) MCQ_ACC(1) MCQ_ACC(2) MCQ_ACC(3) MCQ_ACC(4) MCQ_ACC(5) MCQ_ACC(6) MCQ_ACC(7)
+                    MCQ_ACC(8) MCQ_ACC(9) MCQ_ACC(10) MCQ_ACC(11) MCQ_ACC(12) MCQ_ACC(13) MCQ_ACC(14) MCQ_ACC(15)
+                    default: break;
+                }
+#undef MCQ_ACC
+            }
+        }
+        __syncthreads();
+    }
+    if (my_n < N) {
+        float4 *g = reinterpret_cast<float4 *>(grad + (size_t)my_n * K * D) + my_h * 32 + lane;
+#define MCQ_FLUSH(i) atomicAdd(g + (size_t)i * D4, a##i);
+        MCQ_FLUSH(0) MCQ_FLUSH(1) MCQ_FLUSH(2) MCQ_FLUSH(3) MCQ_FLUSH(4) MCQ_FLUSH(5) MCQ_FLUSH(6) MCQ_FLUSH(7)
+        MCQ_FLUSH(8) MCQ_FLUSH(9) MCQ_FLUSH(10) MCQ_FLUSH(11) MCQ_FLUSH(12) MCQ_FLUSH(13) MCQ_FLUSH(14) MCQ_FLUSH(15)
+#undef MCQ_FLUSH
+    }
+}
+
 template <typename T>
 int recon_fwd_t(const T *x, const int64_t *idx, int64_t B, int N, int K, int D, const float *cs, const float *mean,
                 float *sums, float *partials, cudaStream_t st) {
@@ -318,6 +394,30 @@ int recon_bwd_launch(const T *x, const int64_t *idx, int64_t B, int N, int K, in
 template <typename T>
 int recon_bwd_t(const T *x, const int64_t *idx, int64_t B, int N, int K, int D, const float *cs, const float *coef,
                 float *grad, cudaStream_t st) {
+    if (K == 16 && D % 128 == 0 && (D / 128 <= 4 || D / 128 == 8) && N * (D / 128) <= 16 && B >= 8192 &&
+        !getenv("MCQ_RECON_BWD_ATOMIC")) {
+        const int vc = D / 128;
+        const size_t smem = (size_t)32 * D * sizeof(float);
+        int64_t blocks = (B + 31) / 32;
+        if (blocks > 148) blocks = 148;
+        const unsigned threads = (unsigned)(N * vc * 32);
+#define MCQ_RBK(VC)                                                                                       \
+    do {                                                                                                  \
+        auto kern = recon_bwd_k16_kernel<T, VC>;                                                          \
+        MCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        kern<<<(unsigned)blocks, threads, smem, st>>>(x, idx, B, N, D, cs, coef, grad);                   \
+    } while (0)
+        switch (vc) {
+            case 1: MCQ_RBK(1); break;
+            case 2: MCQ_RBK(2); break;
+            case 3: MCQ_RBK(3); break;
+            case 4: MCQ_RBK(4); break;
+            default: MCQ_RBK(8); break;
+        }
+#undef MCQ_RBK
+        MCQ_LAUNCH_CHECK("recon_bwd_k16_kernel");
+        return MCQ_OK;
+    }
     if (D % 128 == 0) {
         int64_t blocks = (B + 7) / 8;
         if (blocks > RECON_BLOCKS) blocks = RECON_BLOCKS;

@@ -70,6 +70,8 @@ class QuantizerTrainer(object):
         if rec is None:
             seen = self._warm.get(key, 0)
             if seen < self._GRAPH_WARMUP or len(self._graphs) >= self._MAX_GRAPHS:
+                if len(self._warm) > 256:  # ever-changing batch shapes: nothing worth capturing, keep the table small
+                    self._warm.clear()
                 self._warm[key] = seen + 1
                 losses = self._loss_and_update(x, num_iters)
                 self.optim.zero_grad()

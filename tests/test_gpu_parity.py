@@ -682,3 +682,34 @@ def test_trainer_cuda_graph_equals_eager():
     for i in range(6):
         graphed.step(batches[i % len(batches)])
     assert len(graphed._graphs) > 0
+
+
+@pytest.mark.parametrize("N,D,B", [(8, 256, 20000), (4, 128, 9000), (2, 1024, 8192)])
+def test_recon_loss_backward_small_table(N, D, B):
+    """Reconstruction-loss gradient for codebook_size 16 at trainer batch sizes: the register-accumulating kernel
+    (recon_bwd_k16_kernel) against the vector-atomic kernel (MCQ_RECON_BWD_ATOMIC=1) and a PyTorch evaluation."""
+    K = 16
+    p = synth.synth_params(D, N, K, 3)
+    q = make_quantizer(D, N, K, p, DEV, centers_scale=0.01)
+    x = synth.synth_x(B, D, 9, torch.bfloat16).to(DEV)
+    grads = {}
+    for mode in ("regs", "atomic"):
+        if mode == "atomic":
+            os.environ["MCQ_RECON_BWD_ATOMIC"] = "1"
+        try:
+            q.zero_grad()
+            q.compute_loss(x, 1)[0].backward()
+            grads[mode] = (q.centers.grad.clone(), q.centers_scale.grad.clone())
+        finally:
+            os.environ.pop("MCQ_RECON_BWD_ATOMIC", None)
+    q.zero_grad()
+    idx = q._compute_indexes(x, 1)
+    cs = q.get_centers()
+    xf = x.float()
+    xa = sum(cs[n][idx[:, n]] for n in range(N))
+    rel = ((xa - xf) ** 2).sum() / (((xf - q.get_data_mean()) ** 2).sum() + 1e-20)
+    rel.backward()
+    for g in grads.values():
+        assert (g[0] - q.centers.grad).abs().max().item() <= 1e-4 * q.centers.grad.abs().max().item()
+        assert torch.allclose(g[1], q.centers_scale.grad, rtol=1e-4)
+    assert (grads["regs"][0] - grads["atomic"][0]).abs().max().item() <= 1e-5 * grads["atomic"][0].abs().max().item()
