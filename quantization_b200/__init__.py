@@ -3,5 +3,6 @@ danpovey/quantization, behind the reference's `Quantizer` / `QuantizerTrainer` A
 from .quantizer import Quantizer  # noqa: F401
 from .trainer import QuantizerTrainer  # noqa: F401
 from .prediction import JointCodebookLoss  # noqa: F401
+from .data import read_hdf5_data  # noqa: F401
 
-__all__ = ["Quantizer", "QuantizerTrainer", "JointCodebookLoss"]
+__all__ = ["Quantizer", "QuantizerTrainer", "JointCodebookLoss", "read_hdf5_data"]

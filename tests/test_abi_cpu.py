@@ -137,3 +137,40 @@ def test_joint_codebook_loss_mirror_has_the_reference_parameters():
         mod(torch.from_numpy(pred), torch.from_numpy(codes))
     with pytest.raises(AssertionError):
         JointCodebookLoss(8, 1)  # num_codebooks must be > 1 (prediction.py:128)
+
+
+def test_read_hdf5_data_with_a_stand_in_h5py(monkeypatch):
+    """read_hdf5_data (reference quantization.py:744-820) against its definition, with a minimal stand-in for h5py (the
+    package is not in this image): datasets of shape (*, dim) are flattened in key order, cast to float16, shuffled by
+    one np.random.shuffle call, and split into (train, valid) with valid = the first min(5 %, 10000) rows."""
+    import sys
+    import types
+    import numpy as np
+    import torch
+    from quantization_b200 import read_hdf5_data
+
+    rng = np.random.default_rng(0)
+    sets = {"dataset_0": rng.standard_normal((7, 3, 4)).astype(np.float32),
+            "dataset_1": rng.standard_normal((50, 4)).astype(np.float16),
+            "dataset_2": rng.standard_normal((2, 5, 8, 4)).astype(np.float64)}
+
+    class FakeFile(dict):
+        def __init__(self, name, mode):
+            assert mode == "r"
+            super().__init__(sets)
+
+    monkeypatch.setitem(sys.modules, "h5py", types.SimpleNamespace(File=FakeFile))
+    np.random.seed(123)
+    train, valid = read_hdf5_data("whatever.h5")
+    flat = np.concatenate([np.ascontiguousarray(v).reshape(-1, 4).astype(np.float16) for v in sets.values()])
+    np.random.seed(123)
+    np.random.shuffle(flat)
+    n_valid = int(0.05 * len(flat))
+    assert train.dtype == torch.float16 and valid.dtype == torch.float16
+    assert np.array_equal(valid.numpy(), flat[:n_valid]) and np.array_equal(train.numpy(), flat[n_valid:])
+    assert len(flat) == 7 * 3 + 50 + 2 * 5 * 8 and n_valid == 7
+    # the 10000-row cap
+    sets.clear()
+    sets["big"] = np.zeros((250000, 2), dtype=np.float16)
+    train, valid = read_hdf5_data("big.h5")
+    assert valid.shape == (10000, 2) and train.shape == (240000, 2)
