@@ -62,12 +62,13 @@ __global__ void fill_inv_scale_kernel(const unsigned *__restrict__ absmax_bits, 
 }
 
 // planes[p][c][r] (p = 0, 1; c < Cp; r < Rp) = fp16 pieces of scale * X[r][c]; zero outside the matrix.
-// One CTA transposes a 64 (rows) x 64 (columns) tile.
+// One CTA transposes a 64 (rows) x 64 (columns) tile: rows of X are read 256 contiguous bytes at a time, stored
+// transposed in shared memory, and written back as __half2 pairs -- a warp writes 128 contiguous bytes of one plane row.
 template <typename T>
 __global__ void __launch_bounds__(256) pack_transposed_kernel(const T *__restrict__ X, int64_t R, int C, int64_t ld,
                                                               const unsigned *__restrict__ absmax_bits,
                                                               __half *__restrict__ planes, int64_t Rp, int Cp) {
-    __shared__ float tile[64][65];
+    __shared__ __align__(8) float tile[64][66];  // [column][row]
     const float s = scale_for(*absmax_bits);
     const int64_t r0 = (int64_t)blockIdx.x * 64;
     const int c0 = blockIdx.y * 64;
@@ -76,20 +77,21 @@ __global__ void __launch_bounds__(256) pack_transposed_kernel(const T *__restric
     for (int i = ty; i < 64; i += 4) {
         const int64_t r = r0 + i;
         const int c = c0 + tx;
-        tile[i][tx] = (r < R && c < C) ? to_f32(X[r * ld + c]) * s : 0.0f;
+        tile[tx][i] = (r < R && c < C) ? to_f32(X[r * ld + c]) * s : 0.0f;
     }
     __syncthreads();
     const size_t plane = (size_t)Cp * (size_t)Rp;
+    const int rr = threadIdx.x & 31, cc = threadIdx.x >> 5;  // lane: row pair, warp: column
 #pragma unroll 4
-    for (int i = ty; i < 64; i += 4) {
+    for (int i = cc; i < 64; i += 8) {
         const int c = c0 + i;
         if (c < Cp) {
-            const float v = tile[tx][i];
-            const __half h0 = __float2half_rn(v);
-            const __half h1 = __float2half_rn(v - __half2float(h0));
-            const size_t o = (size_t)c * Rp + (size_t)(r0 + tx);
-            planes[o] = h0;
-            planes[plane + o] = h1;
+            const float2 v = *reinterpret_cast<const float2 *>(&tile[i][2 * rr]);
+            const __half a0 = __float2half_rn(v.x), b0 = __float2half_rn(v.y);
+            const __half a1 = __float2half_rn(v.x - __half2float(a0)), b1 = __float2half_rn(v.y - __half2float(b0));
+            const size_t o = (size_t)c * Rp + (size_t)(r0 + 2 * rr);
+            *reinterpret_cast<__half2 *>(planes + o) = __halves2half2(a0, b0);
+            *reinterpret_cast<__half2 *>(planes + plane + o) = __halves2half2(a1, b1);
         }
     }
 }
@@ -185,12 +187,12 @@ TnPlan tn_plan(int64_t R, int C1, int C2) {
     // Short accumulation chains: the tensor core adds every 16-deep product into the fp32 accumulator with a rounding
     // that is not round-to-nearest, so the error grows with the number of accumulations per output.  At most 16
     // k-blocks (1,024 rows, 64 accumulations of the main product) per split keeps it near 2^-20 of sum |a b|; the
-    // partial products cost splits * C1p * C2p * 4 bytes (capped at 256 MB) and one extra pass to sum.
+    // partial products cost splits * C1p * C2p * 4 bytes (capped at 512 MB) and one extra pass to sum.
     int64_t splits = (kb + 15) / 16;
     const int64_t min_splits = (2 * 148 + mn_tiles - 1) / mn_tiles;  // and about two waves of tiles on 148 SMs
     if (splits < min_splits) splits = min_splits;
     if (splits > kb) splits = kb;
-    const int64_t cap = ((int64_t)256 << 20) / ((int64_t)p.C1p * p.C2p * 4);
+    const int64_t cap = ((int64_t)512 << 20) / ((int64_t)p.C1p * p.C2p * 4);
     if (splits > cap) splits = cap;
     if (splits < 1) splits = 1;
     if (splits > 1024) splits = 1024;
