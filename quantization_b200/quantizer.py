@@ -4,7 +4,8 @@ quantization/quantization.py:16-573) with the hot path -- `encode`, `decode`, `_
 
 The class keeps the reference's constructor, parameter names / state_dict keys (`centers`, `logits_scale`,
 `centers_scale`, `id_buf`, `to_logits.weight`, `to_logits.bias`), RNG call order and method signatures, so it is a
-drop-in for that path.  Everything that is not on the hot path (loss arithmetic, diagnostics) stays in PyTorch.
+drop-in for that path.  `compute_loss` runs in the library too (reconstruction term, classifier losses and their
+gradients: recon.cu, loss.cu, gemm_tn.cu); only scalar / (N, K)-sized arithmetic and the diagnostics stay in PyTorch.
 Extensions over the reference (documented in DESIGN.md): float16 / bfloat16 `x` is accepted (the reference raises on
 mixed dtypes; the kernels up-convert exactly, so the result equals the reference on `x.float()`), and
 `encode_host()` takes host tensors.
@@ -364,7 +365,7 @@ class Quantizer(nn.Module):
         powers = K ** torch.arange(r, device=indexes.device)
         return ((indexes.unsqueeze(2).to(torch.int64) // powers) % K).reshape(indexes.shape[0], self.num_codebooks)
 
-    # ------------------------------------------------------------------ training-side (PyTorch; reference :184-242)
+    # ------------------------------------------------------------------ training-side (reference :184-242)
     def compute_loss(self, x: Tensor, refine_indexes_iters: int = 0):
         """Returns (rel_reconstruction_loss, logprob_loss, logits_entropy_loss, index_entropy_loss) exactly as the
         reference defines them (quantization.py:184-242); only the index search and the decode gather run in the
