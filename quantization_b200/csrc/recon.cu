@@ -275,7 +275,8 @@ __global__ void __launch_bounds__(256) recon_bwd4_kernel(const T *__restrict__ x
 // keeps the 16 rows of that codebook as 16 float4 accumulators per lane and adds each staged frame into the one its
 // (warp-uniform) code selects; one round of vector atomics per CTA at the end.  Measured 119 us at 65,536 frames x 8
 // codebooks (the atomic kernel: 142-149 us); what remains is the latency of staging a tile (16 warps per SM at 128
-// registers, two barriers per 32 frames) -- double-buffering the tile is the next step. ----
+// registers, two barriers per 32 frames) -- double-buffering the tile is the next step.  (Measured and dropped: 32
+// warps per CTA with float2 accumulators, i.e. half the register state per warp: 136 us.) ----
 template <typename T, int VC>
 __global__ void __launch_bounds__(512, 1) recon_bwd_k16_kernel(const T *__restrict__ x, const int64_t *__restrict__ idx,
                                                                int64_t B, int N, int D, const float *__restrict__ cs,

@@ -417,7 +417,7 @@ class Quantizer(nn.Module):
     def _compute_loss_tail_torch(self, xf: Tensor, indexes: Tensor, rel_reconstruction_loss: Tensor):
         """The reference's own formulation of the classifier-side losses (quantization.py:218-240), used for shapes
         the fused kernels do not cover or do not pay off for (empty batches, codebook_size > 256 as produced by
-        get_product_quantizer on K = 256 quantizers, codebook_size < 32).  Plain PyTorch on device tensors."""
+        get_product_quantizer on K = 256 quantizers, codebook_size < 16).  Plain PyTorch on device tensors."""
         N, K = self.num_codebooks, self.codebook_size
         logits = self._logits(xf).reshape(-1, N, K).log_softmax(dim=2)
         chosen = torch.gather(logits, dim=2, index=indexes.unsqueeze(2))
