@@ -211,6 +211,14 @@ int mcq_search(const float *P, const float *gram, int64_t num_frames, int num_co
 int mcq_profile(int enable);
 int mcq_profile_read(double *ms_by_kind, int64_t *launches_by_kind);
 
+/* Work actually done by the refinement search on a workspace: the search kernels add, into a counter block at the
+ * start of the workspace they are given, the number of refinement passes they executed (a frame whose pass returns
+ * its input has converged and skips the remaining passes -- exact) and the number of frames searched.
+ * passes_frames (host, 2 x uint64, may be NULL) receives the totals since the last reset (synchronises `stream`);
+ * reset != 0 zeroes them afterwards.  A fresh workspace holds garbage there: reset before relying on the totals.
+ * Used by bench.py for the roofline accounting ("count only passes actually executed"). */
+int mcq_search_stats(void *workspace, int reset, uint64_t *passes_frames, void *stream);
+
 /*
  * Host-buffer encode: x_host (B, D) and codes_host live in HOST memory (pinned or pageable).  The library
  * stages chunks through its own pinned buffers and device workspace on `device`, overlapping H2D, compute

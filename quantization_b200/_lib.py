@@ -68,6 +68,7 @@ def lib():
         "mcq_jcl_cross_entropy": (i32, [vp, vp, vp, i32, i64, i32, i32, i64, i32, vp, vp, vp, vp]),
         "mcq_profile": (i32, [i32]),
         "mcq_profile_read": (i32, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
+        "mcq_search_stats": (i32, [vp, i32, ctypes.POINTER(ctypes.c_uint64), vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)  # AttributeError here == the library does not export what mcq.h declares
@@ -84,7 +85,7 @@ EXPORTS = ["mcq_version", "mcq_last_error", "mcq_packed_cols", "mcq_prepared_byt
            "mcq_recon_loss_partials", "mcq_recon_loss_forward", "mcq_recon_loss_backward",
            "mcq_gemm_tn_workspace_bytes", "mcq_gemm_tn", "mcq_gemm_nt_workspace_bytes", "mcq_gemm_nt",
            "mcq_jcl_hidden_forward", "mcq_jcl_hidden_backward", "mcq_jcl_partials", "mcq_jcl_cross_entropy",
-           "mcq_profile", "mcq_profile_read"]
+           "mcq_profile", "mcq_profile_read", "mcq_search_stats"]
 
 
 def check(rc, what):
@@ -130,6 +131,15 @@ def profile_read():
     n = (ctypes.c_int64 * 4)()
     check(lib().mcq_profile_read(ms, n), "mcq_profile_read")
     return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(PROF_KINDS)}
+
+
+def search_stats(workspace: torch.Tensor, reset: bool = False, read: bool = True):
+    """(refinement passes executed, frames searched) accumulated in `workspace` since the last reset (mcq.h)."""
+    out = (ctypes.c_uint64 * 2)()
+    with torch.cuda.device(workspace.device):
+        check(lib().mcq_search_stats(workspace.data_ptr(), 1 if reset else 0, out if read else None,
+                                     stream_ptr(workspace.device)), "mcq_search_stats")
+    return (int(out[0]), int(out[1])) if read else None
 
 
 def gemm_tn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

@@ -70,6 +70,7 @@ Workspace workspace_layout(int64_t Bc, int N, int K, int D) {
     const size_t Dp = align_up((size_t)D, 64), NK = (size_t)N * K;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    W.off_ctr = take(1024);  // first, so that its place does not depend on the chunk size (mcq_search_stats)
     W.off_xf = take(sizeof(float) * (size_t)W.Mp * D);
     W.off_xsplit = take(sizeof(__half) * 2 * (size_t)W.Mp * Dp);
     W.off_lsplit = take(sizeof(__half) * 2 * (size_t)W.Mp * Dp);
@@ -77,7 +78,6 @@ Workspace workspace_layout(int64_t Bc, int N, int K, int D) {
     W.off_lscale = take(sizeof(float) * (size_t)W.Mp);
     W.off_p = take(sizeof(float) * (size_t)W.Mp * NK);
     W.off_idx = take(sizeof(int32_t) * (size_t)W.Mp * N);
-    W.off_ctr = take(1024);
     W.bytes = off;
     return W;
 }
@@ -199,6 +199,21 @@ int mcq_profile_read(double *ms_by_kind, int64_t *launches_by_kind) {
     return MCQ_OK;
 }
 const char *mcq_last_error(void) { return g_err; }
+
+int mcq_search_stats(void *workspace, int reset, uint64_t *passes_frames, void *stream) {
+    if (!workspace) {
+        set_error("mcq_search_stats: null workspace");
+        return MCQ_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char *blk = (char *)workspace + sizeof(unsigned) * SEARCH_STAT_WORD;
+    if (passes_frames) {
+        MCQ_CUDA(cudaMemcpyAsync(passes_frames, blk, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        MCQ_CUDA(cudaStreamSynchronize(st));
+    }
+    if (reset) MCQ_CUDA(cudaMemsetAsync(blk, 0, 2 * sizeof(uint64_t), st));
+    return MCQ_OK;
+}
 
 int mcq_packed_cols(int N, int K) {
     long k = K;
@@ -445,11 +460,14 @@ int mcq_class_loss_forward(const void *x, int x_dtype, int64_t B, int D, int N, 
         float *out = xw + (size_t)b0 * L.NK;  // chunk starts are multiples of 128 rows: the GEMM writes in place
         if ((rc = PROF(MCQ_PROF_OTHER, st, launch_split_x(xc, x_dtype, nb, L, blob, W, ws, true, st)))) return rc;
         if (tc) {
+            // only the first mp rows of the chunk's split buffer take part; its second fp16 plane starts W.Mp rows
+            // (not mp rows) after the first, whatever the size of this -- possibly last, shorter -- chunk
             const int64_t mp = (int64_t)align_up((size_t)nb, 128);
             rc = PROF(MCQ_PROF_GEMM, st,
-                      launch_gemm_tc((const __half *)(ws + W.off_lsplit), (const float *)(ws + W.off_lscale),
-                                     (const __half *)(blob + L.off_wsplit), (const float *)(blob + L.off_wscale), out,
-                                     mp, L.NK, L.Dp, st));
+                      launch_gemm_tc_general((const __half *)(ws + W.off_lsplit), (const float *)(ws + W.off_lscale),
+                                             (const __half *)(blob + L.off_wsplit),
+                                             (const float *)(blob + L.off_wscale), out, L.NK, nb, mp, L.NK, L.Dp, 0, st,
+                                             W.Mp));
         } else {
             rc = PROF(MCQ_PROF_GEMM, st,
                       launch_gemm_ffma((const float *)(ws + W.off_xf), (const float *)(blob + L.off_w), out, nb, L.NK,

@@ -57,7 +57,7 @@ struct Workspace {
     size_t off_lscale; // float [Mp]  ... of each fl(logits_scale * x) row
     size_t off_p;      // float [Mp*NK]     P = x Cs^T   (also receives the logits before P is formed)
     size_t off_idx;    // int32 [Mp*N]
-    size_t off_ctr;    // uint32 [256]      work counter of the search kernel (dynamic frame scheduling)
+    size_t off_ctr;    // uint32 [256]      counter block of the search kernel (always offset 0; see SEARCH_STAT_WORD)
     size_t bytes;
 };
 
@@ -83,13 +83,29 @@ int launch_gemm_tc_splitk(const __half *a_split, const float *a_scale, const __h
                           float *C, int64_t Mp, int NK, int Dp, int k_splits, cudaStream_t st);
 int launch_gemm_tc_general(const __half *a_split, const float *a_scale, const __half *b_split, const float *b_scale,
                            float *C, int64_t ldc, int64_t m_valid, int64_t Mp, int NK, int Dp, int accumulate,
-                           cudaStream_t st);
+                           cudaStream_t st, int64_t a_plane_rows = 0);
 int launch_gemm_tc_argmax(const __half *a_split, const float *a_scale, const __half *b_split, const float *b_scale,
                           int64_t Mp, int NK, int Dp, const float *bias, int64_t B, int N, int K, void *scratch,
                           int32_t *idx, cudaStream_t st);
 int launch_argmax_init(const float *logits, const float *bias, int64_t B, int N, int K, int32_t *idx, cudaStream_t st);
 // work_counter (optional, device, zeroed by the caller on `st`): lets the warps of the search kernel fetch frames
 // dynamically instead of striding over the batch (frames take 2..iters passes, so static striding leaves a tail)
+// Layout of the counter block `work_counter` points at (the first 1024 bytes of a workspace): word 0 = the frame
+// counter of the current launch (zeroed by the caller per launch); bytes 8..23 = two uint64 running totals the search
+// kernels add to -- refinement passes executed, frames searched -- which nobody resets (bench.py zeroes / reads them
+// to count the passes that actually ran: converged frames stop early).
+constexpr int SEARCH_STAT_WORD = 2;  // offset (in 32-bit words) of the two uint64 totals
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void search_stats_add(unsigned *work_counter, unsigned npass, unsigned nframes, int lane) {
+    if (work_counter != nullptr && lane == 0 && nframes != 0) {
+        unsigned long long *st = reinterpret_cast<unsigned long long *>(work_counter + SEARCH_STAT_WORD);
+        atomicAdd(st, (unsigned long long)npass);
+        atomicAdd(st + 1, (unsigned long long)nframes);
+    }
+}
+#endif
+
 int launch_search(const float *P, const float *gram, int64_t B, int N, int K, int iters, const int32_t *idx_in,
                   int32_t *idx_out, cudaStream_t st, unsigned *work_counter = nullptr);
 // second version of the search (search2.cu): codebook_size 256, 2/4/8 codebooks

@@ -374,12 +374,16 @@ int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint
 template <int BN, bool ARGMAX>
 int launch_bn(const __half *a_split, const float *a_scale, const __half *b_split, const float *b_scale, float *C,
               int64_t Mp, int NK, int Dp, cudaStream_t st, const float *bias = nullptr, float *part_val = nullptr,
-              int *part_idx = nullptr, int k_splits = 1, int64_t ldc = 0, int64_t m_valid = -1, int accumulate = 0) {
+              int *part_idx = nullptr, int k_splits = 1, int64_t ldc = 0, int64_t m_valid = -1, int accumulate = 0,
+              int64_t a_plane_rows = 0) {
+    // a_plane_rows: row distance between the two fp16 planes of A (default Mp; larger when only the first Mp rows of
+    // a bigger split buffer take part, e.g. the tail chunk of a batch)
     using Cfg = TcCfg<BN>;
     const uint64_t NKp = align_up((size_t)NK, 128);
+    if (a_plane_rows <= 0) a_plane_rows = Mp;
     CUtensorMap ma, mb;
     int rc;
-    if ((rc = make_map(&ma, a_split, (uint64_t)PLANES * (uint64_t)Mp, (uint64_t)Dp, BM))) return rc;
+    if ((rc = make_map(&ma, a_split, (uint64_t)PLANES * (uint64_t)a_plane_rows, (uint64_t)Dp, BM))) return rc;
     if ((rc = make_map(&mb, b_split, (uint64_t)PLANES * NKp, (uint64_t)Dp, BN))) return rc;
     auto kern = gemm_fp16x2_kernel<BN, ARGMAX>;
     MCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
@@ -390,7 +394,7 @@ int launch_bn(const __half *a_split, const float *a_scale, const __half *b_split
     int64_t tiles = (int64_t)m_tiles * n_tiles * k_splits;
     int grid = (int)(tiles < sms ? tiles : sms);
     kern<<<grid, NUM_THREADS, Cfg::SMEM, st>>>(ma, mb, C, m_tiles, n_tiles, Dp / BK / k_splits, ldc > 0 ? (int)ldc : NK,
-                                               (int)Mp, (int)NKp, a_scale, b_scale, bias, part_val, part_idx, k_splits,
+                                               (int)a_plane_rows, (int)NKp, a_scale, b_scale, bias, part_val, part_idx, k_splits,
                                                (size_t)Mp * (size_t)NK, m_valid >= 0 ? (int)m_valid : (int)Mp, accumulate);
     MCQ_LAUNCH_CHECK("gemm_fp16x2_kernel");
     return MCQ_OK;
@@ -426,17 +430,18 @@ int launch_gemm_tc_splitk(const __half *a_split, const float *a_scale, const __h
 // General form: C (m_valid x NK, row stride ldc) = or += A . B^T from packed operands (Mp = m_valid rounded up to 128).
 int launch_gemm_tc_general(const __half *a_split, const float *a_scale, const __half *b_split, const float *b_scale,
                            float *C, int64_t ldc, int64_t m_valid, int64_t Mp, int NK, int Dp, int accumulate,
-                           cudaStream_t st) {
+                           cudaStream_t st, int64_t a_plane_rows) {
     if (Mp <= 0) return MCQ_OK;
-    if (Mp % BM != 0 || Dp % BK != 0 || NK % 64 != 0 || ldc < NK || (ldc & 3) || m_valid > Mp) {
+    if (Mp % BM != 0 || Dp % BK != 0 || NK % 64 != 0 || ldc < NK || (ldc & 3) || m_valid > Mp ||
+        (a_plane_rows > 0 && a_plane_rows < Mp)) {
         set_error("gemm_tc_general: Mp=%lld Dp=%d NK=%d ldc=%lld not supported", (long long)Mp, Dp, NK, (long long)ldc);
         return MCQ_EINVAL;
     }
     if (NK % 128 == 0)
         return launch_bn<128, false>(a_split, a_scale, b_split, b_scale, C, Mp, NK, Dp, st, nullptr, nullptr, nullptr, 1,
-                                     ldc, m_valid, accumulate);
+                                     ldc, m_valid, accumulate, a_plane_rows);
     return launch_bn<64, false>(a_split, a_scale, b_split, b_scale, C, Mp, NK, Dp, st, nullptr, nullptr, nullptr, 1, ldc,
-                                m_valid, accumulate);
+                                m_valid, accumulate, a_plane_rows);
 }
 
 // idx[b][n] = first maximum over the K / 128 tile maxima of codebook n (ascending tile = ascending column order)

@@ -33,31 +33,11 @@ int grow(void **p, size_t *cap, size_t need) {
     return MCQ_OK;
 }
 
-}  // namespace
-
-}  // namespace mcq
-
-using namespace mcq;
-
-extern "C" int mcq_encode_host(const void *x_host, int x_dtype, int64_t B, int D, int N, int K, const void *prepared,
-                               int iters, void *codes_host, int codes_dtype, int device) {
-    int rc = check_shape(N, K, D);
-    if (rc) return rc;
-    if (B < 0 || iters < 0 || x_dtype < 0 || x_dtype > 2 || codes_dtype < 0 || codes_dtype > 2 || device < 0 ||
-        device >= MAX_DEV) {
-        set_error("mcq_encode_host: bad argument");
-        return MCQ_EINVAL;
-    }
-    if (B == 0) return MCQ_OK;
-    if (!x_host || !prepared || !codes_host) {
-        set_error("mcq_encode_host: null pointer");
-        return MCQ_EINVAL;
-    }
-    std::lock_guard<std::mutex> lock(g_mu[device]);
-    int prev_dev = 0;
-    MCQ_CUDA(cudaGetDevice(&prev_dev));
-    MCQ_CUDA(cudaSetDevice(device));
-    HostCtx &c = g_ctx[device];
+// The body of mcq_encode_host with the device selected and the context locked; may return early on any error (the
+// caller synchronises the streams and restores the device).
+int encode_host_locked(HostCtx &c, const void *x_host, int x_dtype, int64_t B, int D, int N, int K,
+                       const void *prepared, int iters, void *codes_host, int codes_dtype) {
+    int rc = MCQ_OK;
     if (!c.init) {
         MCQ_CUDA(cudaStreamCreateWithFlags(&c.s_in, cudaStreamNonBlocking));
         MCQ_CUDA(cudaStreamCreateWithFlags(&c.s_cmp, cudaStreamNonBlocking));
@@ -102,8 +82,52 @@ extern "C" int mcq_encode_host(const void *x_host, int x_dtype, int64_t B, int D
                                  (size_t)nb * ncols * celt, cudaMemcpyDeviceToHost, c.s_out));
         MCQ_CUDA(cudaEventRecord(c.ev_out[k], c.s_out));
     }
-    MCQ_CUDA(cudaStreamSynchronize(c.s_out));
-    MCQ_CUDA(cudaStreamSynchronize(c.s_cmp));
-    MCQ_CUDA(cudaSetDevice(prev_dev));
     return MCQ_OK;
+}
+
+}  // namespace
+
+}  // namespace mcq
+
+using namespace mcq;
+
+extern "C" int mcq_encode_host(const void *x_host, int x_dtype, int64_t B, int D, int N, int K, const void *prepared,
+                               int iters, void *codes_host, int codes_dtype, int device) {
+    int rc = check_shape(N, K, D);
+    if (rc) return rc;
+    if (B < 0 || iters < 0 || x_dtype < 0 || x_dtype > 2 || codes_dtype < 0 || codes_dtype > 2 || device < 0 ||
+        device >= MAX_DEV) {
+        set_error("mcq_encode_host: bad argument");
+        return MCQ_EINVAL;
+    }
+    if (B == 0) return MCQ_OK;
+    if (!x_host || !prepared || !codes_host) {
+        set_error("mcq_encode_host: null pointer");
+        return MCQ_EINVAL;
+    }
+    std::lock_guard<std::mutex> lock(g_mu[device]);
+    int prev_dev = 0;
+    MCQ_CUDA(cudaGetDevice(&prev_dev));
+    MCQ_CUDA(cudaSetDevice(device));
+    // ONE exit path: whatever happens below, nothing is left in flight on the three streams (they touch the caller's
+    // host buffers and the cached device buffers, which a later call may free and re-grow) and the caller's current
+    // device is restored.
+    struct Cleanup {
+        HostCtx &c;
+        int prev_dev;
+        ~Cleanup() {
+            if (c.s_in) cudaStreamSynchronize(c.s_in);
+            if (c.s_cmp) cudaStreamSynchronize(c.s_cmp);
+            if (c.s_out) cudaStreamSynchronize(c.s_out);
+            cudaSetDevice(prev_dev);
+        }
+    } cleanup{g_ctx[device], prev_dev};
+    rc = encode_host_locked(g_ctx[device], x_host, x_dtype, B, D, N, K, prepared, iters, codes_host, codes_dtype);
+    if (rc == MCQ_OK) {
+        // report asynchronous failures of the last copies / kernels instead of swallowing them in the guard
+        cudaError_t e = cudaStreamSynchronize(g_ctx[device].s_out);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx[device].s_cmp);
+        if (e != cudaSuccess) rc = cuda_fail(e, "mcq_encode_host: stream synchronisation");
+    }
+    return rc;
 }

@@ -903,6 +903,7 @@ __global__ void __launch_bounds__(WPC16 * 32, MCQ_S16_MINB)
     s.sel[lane] = make_float2(0.0f, __int_as_float(0));
     __syncwarp();
     const int64_t nwarps = (int64_t)gridDim.x * WPC16;
+    unsigned npass = 0, nframes = 0;
     for (int64_t b = (int64_t)blockIdx.x * WPC16 + warp; b < B;) {
         if (lane < 16) s.old[lane] = idx_in[(size_t)b * 16 + lane];
         __syncwarp();
@@ -912,8 +913,10 @@ __global__ void __launch_bounds__(WPC16 * 32, MCQ_S16_MINB)
             const int prev = (lane < 16) ? s.old[lane] : 0;
             refine_pass16(s, Pb, G, lane);
             const int now = (lane < 16) ? s.old[lane] : 0;
+            ++npass;
             if (__all_sync(FULL, prev == now)) break;  // fixed point: the remaining passes are no-ops
         }
+        ++nframes;
         if (lane < 16) idx_out[(size_t)b * 16 + lane] = s.old[lane];
         if (work_counter != nullptr) {
             unsigned t = 0;
@@ -924,6 +927,7 @@ __global__ void __launch_bounds__(WPC16 * 32, MCQ_S16_MINB)
         }
         __syncwarp();
     }
+    search_stats_add(work_counter, npass, nframes, lane);
 }
 
 int launch16(const float *P, const float *Gp, int64_t B, int iters, const int32_t *idx_in, int32_t *idx_out,
@@ -968,6 +972,7 @@ __global__ void __launch_bounds__(Launch2<N>::WPC * 32, Launch2<N>::MINB)
     // the first frame of a warp is its global warp index; further frames come from the work counter when there is
     // one (frames take 2..iters passes, so static striding would leave a tail), else by striding over the batch
     const int64_t nwarps = (int64_t)gridDim.x * wpc;
+    unsigned npass = 0, nframes = 0;
     for (int64_t b = (int64_t)blockIdx.x * wpc + warp; b < B;) {
         if (lane < N) s.old[lane] = idx_in[(size_t)b * N + lane];
         __syncwarp();
@@ -977,9 +982,11 @@ __global__ void __launch_bounds__(Launch2<N>::WPC * 32, Launch2<N>::MINB)
             const int prev = (lane < N) ? s.old[lane] : 0;
             refine_pass2<N>(s, Pb, G, lane);
             const int now = (lane < N) ? s.old[lane] : 0;
+            ++npass;
             // a pass that returns its input is a fixed point of a deterministic map: the remaining passes are no-ops
             if (__all_sync(FULL, prev == now)) break;
         }
+        ++nframes;
         if (lane < N) idx_out[(size_t)b * N + lane] = s.old[lane];
         if (work_counter != nullptr) {
             unsigned t = 0;
@@ -990,6 +997,7 @@ __global__ void __launch_bounds__(Launch2<N>::WPC * 32, Launch2<N>::MINB)
         }
         __syncwarp();
     }
+    search_stats_add(work_counter, npass, nframes, lane);
 }
 
 template <int N>

@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(WPC * 32, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpK16 &s = wm[warp];
     const int64_t nwarps = (int64_t)gridDim.x * WPC;
+    unsigned npass = 0, nframes = 0;
     for (int64_t b = (int64_t)blockIdx.x * WPC + warp; b < B;) {
         if (lane < NQ) s.old[lane] = idx_in[(size_t)b * NQ + lane];
         __syncwarp();
@@ -251,8 +252,10 @@ __global__ void __launch_bounds__(WPC * 32, 1)
             const int prev = (lane < NQ) ? s.old[lane] : 0;
             pass_k16(s, Gs, diag, Pb, lane);
             const int now = (lane < NQ) ? s.old[lane] : 0;
+            ++npass;
             if (__all_sync(FULL, prev == now)) break;  // fixed point: the remaining passes are no-ops
         }
+        ++nframes;
         if (lane < NQ) idx_out[(size_t)b * NQ + lane] = s.old[lane];
         if (work_counter != nullptr) {
             unsigned t = 0;
@@ -263,6 +266,7 @@ __global__ void __launch_bounds__(WPC * 32, 1)
         }
         __syncwarp();
     }
+    search_stats_add(work_counter, npass, nframes, lane);
 }
 
 }  // namespace

@@ -28,6 +28,10 @@ def _is_power_of_two(n: int) -> bool:
 
 # smallest codebook_size that takes the fused classifier-loss kernels (below it: the PyTorch formulation)
 _FUSED_LOSS_MIN_K = int(os.environ.get("MCQ_FUSED_LOSS_MIN_K", "16"))
+_CHECK_INDEXES = os.environ.get("MCQ_CHECK_INDEXES", "0") == "1"
+# largest shapes the search kernels cover (csrc/api.cu check_shape); the reference itself has no such limit
+MAX_CODEBOOK_SIZE = 256
+MAX_NUM_CODEBOOKS = 64
 
 
 class _DecodeFn(torch.autograd.Function):
@@ -204,6 +208,13 @@ class Quantizer(nn.Module):
 
     def _prepared(self) -> Tensor:
         """The prepared blob (scaled centers, Gram table, operand splits), rebuilt when any parameter changes."""
+        if self.codebook_size > MAX_CODEBOOK_SIZE or self.num_codebooks > MAX_NUM_CODEBOOKS:
+            # e.g. get_product_quantizer() of a codebook_size-256 quantizer: constructible (as in the reference), but
+            # there is no kernel for it and no PyTorch fallback by design
+            raise NotImplementedError(
+                f"codebook_size={self.codebook_size} / num_codebooks={self.num_codebooks}: the CUDA search kernels "
+                f"cover codebook_size <= {MAX_CODEBOOK_SIZE} and num_codebooks <= {MAX_NUM_CODEBOOKS} "
+                "(every shape QuantizerTrainer produces); there is no CPU / PyTorch fallback")
         ps = self._params()
         dev = self.centers.device
         _lib.require_cuda(self.centers, "Quantizer parameters")
@@ -336,7 +347,9 @@ class Quantizer(nn.Module):
         if ncols != N:
             r = N // max(ncols, 1)
             assert ncols > 0 and N % ncols == 0 and r in (2, 4, 8, 16)  # reference :566
-        if idx.dtype != torch.uint8 and B > 0:
+        if _CHECK_INDEXES and idx.dtype != torch.uint8 and B > 0:
+            # debugging aid only (MCQ_CHECK_INDEXES=1): a blocking host round trip on an HBM-bound path, and it
+            # would make decode uncapturable in a CUDA graph.  The kernel clamps out-of-range codes to entry 0.
             hi = K ** (N // ncols)
             if bool(((idx < 0) | (idx >= hi)).any()):
                 raise IndexError(f"decode: indexes out of range [0, {hi})")
@@ -389,7 +402,7 @@ class Quantizer(nn.Module):
 
         N, K = self.num_codebooks, self.codebook_size
         B = x.shape[0]
-        if B == 0 or K > 256 or K < _FUSED_LOSS_MIN_K:
+        if B == 0 or K < _FUSED_LOSS_MIN_K:
             # (K = 16, trainer phase 1, also takes the fused kernels: 1.49 vs 1.89 ms of kernels per step at 65,536 frames)
             xf = x.float() if x.dtype != torch.float32 else x
             return self._compute_loss_tail_torch(xf, indexes, rel_reconstruction_loss)
@@ -416,8 +429,8 @@ class Quantizer(nn.Module):
 
     def _compute_loss_tail_torch(self, xf: Tensor, indexes: Tensor, rel_reconstruction_loss: Tensor):
         """The reference's own formulation of the classifier-side losses (quantization.py:218-240), used for shapes
-        the fused kernels do not cover or do not pay off for (empty batches, codebook_size > 256 as produced by
-        get_product_quantizer on K = 256 quantizers, codebook_size < 16).  Plain PyTorch on device tensors."""
+        the fused kernels do not pay off for (empty batches, a single codebook of fewer than 16 entries).  Plain
+        PyTorch on device tensors."""
         N, K = self.num_codebooks, self.codebook_size
         logits = self._logits(xf).reshape(-1, N, K).log_softmax(dim=2)
         chosen = torch.gather(logits, dim=2, index=indexes.unsqueeze(2))

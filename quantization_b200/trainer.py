@@ -61,6 +61,14 @@ class QuantizerTrainer(object):
         self.optim.step()
         return losses
 
+    def _eager_update(self, x: torch.Tensor, num_iters: int):
+        """One eager step.  The gradients are cleared BEFORE the backward as well: after a capture / replay `p.grad`
+        may still point at a graph's buffers holding the previous replay's gradients."""
+        self.optim.zero_grad(set_to_none=True)
+        losses = self._loss_and_update(x, num_iters)
+        self.optim.zero_grad(set_to_none=True)
+        return losses
+
     def _graphed_update(self, x: torch.Tensor, num_iters: int):
         key = self._graph_key(x, num_iters)
         if self._graphs and next(iter(self._graphs))[-1] != key[-1]:
@@ -73,9 +81,7 @@ class QuantizerTrainer(object):
                 if len(self._warm) > 256:  # ever-changing batch shapes: nothing worth capturing, keep the table small
                     self._warm.clear()
                 self._warm[key] = seen + 1
-                losses = self._loss_and_update(x, num_iters)
-                self.optim.zero_grad()
-                return losses
+                return self._eager_update(x, num_iters)
             q = self.quantizer
             static_x = x.clone()
             self.optim.zero_grad(set_to_none=True)
@@ -88,10 +94,7 @@ class QuantizerTrainer(object):
                 logging.warning(f"QuantizerTrainer: CUDA-graph capture failed ({e}); continuing without graphs")
                 self._use_graph = False
                 self._graphs.clear()
-                self.optim.zero_grad(set_to_none=True)
-                losses = self._loss_and_update(x, num_iters)
-                self.optim.zero_grad()
-                return losses
+                return self._eager_update(x, num_iters)
             # the captured kernels hold raw pointers into these caller-owned buffers: keep them alive with the graph
             keep = [q._prep_blob, q._ws] + [p.grad for p in q.parameters()]
             rec = (graph, static_x, losses, keep)
@@ -100,6 +103,10 @@ class QuantizerTrainer(object):
         static_x.copy_(x)
         graph.replay()
         self.quantizer._prep_key = None  # the parameters changed without their version counters moving
+        # like the reference after its optim.zero_grad() (:681): no gradient is left on the parameters.  The graph
+        # keeps writing into its own buffers (held by `keep`); an eager backward must never accumulate onto them.
+        for p in self.quantizer.parameters():
+            p.grad = None
         return losses
 
     def step(self, x: torch.Tensor) -> None:
@@ -116,8 +123,7 @@ class QuantizerTrainer(object):
              index_entropy_loss) = self._graphed_update(x.contiguous(), num_iters)
         else:
             (reconstruction_loss, logprob_loss, logits_entropy_loss,
-             index_entropy_loss) = self._loss_and_update(x, num_iters)
-            self.optim.zero_grad()
+             index_entropy_loss) = self._eager_update(x, num_iters)
 
         if diagnostics:
             phase = 1 if self.cur_iter <= self.phase_one_iters else 2
