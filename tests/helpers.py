@@ -79,3 +79,66 @@ def jcl_case(g, meta, name):
     pred = g[name + "/pred"].reshape(-1, m["P"])
     codes = g[name + "/codes"].reshape(-1, m["N"])
     return m, pred, codes, par, grads
+
+
+# ---- round 2 ---------------------------------------------------------------------------------------------------------
+
+def load_npz(name):
+    """(arrays, meta) of a tests/golden/*.npz fixture that carries a `meta_json` entry."""
+    g = np.load(os.path.join(GOLDEN_DIR, name))
+    return g, json.loads(bytes(g["meta_json"]).decode())
+
+
+def reference_package():
+    """The unmodified reference package, pip-installed into the git-ignored baseline/_ref (it travels to the GPU box
+    with the snapshot; /root/reference itself does not exist there), or None.  Only used to run the reference LIVE on
+    the GPU beside the product in the full-size parity tests."""
+    import sys
+    import types
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "quantization")):
+        return None
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))  # imported by the reference for read_hdf5_data only
+    sys.path.insert(0, ref_dir)
+    try:
+        import quantization as refq
+        return refq
+    except Exception:
+        return None
+    finally:
+        sys.path.remove(ref_dir)
+
+
+def fp64_errors(idx, x, scaled_centers, rows):
+    """Per-frame squared reconstruction error, evaluated in float64, of the int codes idx[rows] (B', N)."""
+    c64 = np.asarray(scaled_centers, dtype=np.float64)
+    x64 = np.asarray(x, dtype=np.float64)[rows]
+    rec = sum(c64[n, np.asarray(idx)[rows, n]] for n in range(c64.shape[0]))
+    return ((rec - x64) ** 2).sum(1)
+
+
+def disagreement(idx_a, idx_b, x, scaled_centers):
+    """Frames on which two code sets differ and, on those, err64(a) / err64(b).  Returns (rows, ratios)."""
+    rows = np.nonzero((np.asarray(idx_a) != np.asarray(idx_b)).any(1))[0]
+    if rows.size == 0:
+        return rows, np.zeros(0)
+    ea = fp64_errors(idx_a, x, scaled_centers, rows)
+    eb = fp64_errors(idx_b, x, scaled_centers, rows)
+    return rows, ea / np.maximum(eb, 1e-300)
+
+
+def trainer_quality_data(kind, dim):
+    """The batch generator of tests/golden/make_golden_r2.py::trainer_data (same seeds, same order of RNG use):
+    'mlp' = the data of the reference's own trainer test (test_quantization.py:15-22, 31-33), 'gauss' = :66-67."""
+    from torch import nn
+    gen = torch.Generator().manual_seed(4242)
+    if kind == "mlp":
+        model = nn.Sequential(nn.Linear(dim, dim), nn.ReLU(), nn.Linear(dim, dim), nn.ReLU(), nn.LayerNorm(dim),
+                              nn.Linear(dim, dim))
+
+        def f(b):
+            with torch.no_grad():
+                x = torch.randn(b, dim, generator=gen)
+                return model(x) + 0.05 * x
+        return f
+    return lambda b: torch.randn(b, dim, generator=gen)

@@ -1,0 +1,272 @@
+"""Round-2 GPU tests (-m gpu): parity against the reference WITH a control (the reference against its own
+feature-permuted self), full-size parity against the reference run live on the same GPU, the trainer's end quality
+against a reference-trained run, and the regressions the round-1 review asked for (stale gradients around CUDA-graph
+replays, the tail chunk of the classifier-loss GEMM, get_product_quantizer / compute_codebook_correlations values)."""
+import os
+import random
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from quantization_b200 import Quantizer, QuantizerTrainer, _lib, synth
+from helpers import (disagreement, load_npz, make_quantizer, reference_package, trainer_quality_data)
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _record(kind, name, payload):
+    import json
+    try:
+        os.makedirs(os.path.join(_ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(_ROOT, "gpurun_out", "measurements.jsonl"), "a") as f:
+            f.write(json.dumps({"kind": kind, "case": name, **payload}) + "\n")
+    except OSError:
+        pass
+
+
+def _width(ratios):
+    """Spread of fp64 error ratios around 1: the largest |log ratio|."""
+    return float(np.abs(np.log(ratios)).max()) if len(ratios) else 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Parity criterion with a control.  SURVEY 8(c) asked: differing-frame rate <= 1e-4 and, on every differing frame, our
+# fp64 error <= the reference's x (1 + 1e-5).  The second half cannot hold for ANY fp32 implementation that sums in a
+# different order -- the reference fails it against itself: permuting the feature dimension of x / centers / weights
+# consistently (the same function, another fp32 summation order) changes 4..7 of 65,536 frames, with error ratios on
+# both sides of 1.  That control is the yardstick: our differences from the reference must be no more frequent than
+# twice the control's and no wider than the control's.
+
+def test_parity_against_reference_with_control():
+    g, m = load_npz("golden_control.npz")
+    D, N, K, B = m["D"], m["N"], m["K"], m["B"]
+    p = synth.synth_params(D, N, K, m["seed_p"])
+    x = synth.synth_x(B, D, m["seed_x"])
+    assert synth.sha256_of(x) == m["sha_x"] and synth.sha256_of(p["centers"], p["weight"], p["bias"]) == m["sha_params"]
+    ref = g["codes_ref"].astype(np.int64)
+    cs = p["centers"].numpy()
+    # the control: the reference against its permuted selves
+    ctl_counts, ctl_ratios = [], []
+    for ps in m["perm_seeds"]:
+        rows, ratios = disagreement(g[f"codes_perm{ps}"].astype(np.int64), ref, x.numpy(), cs)
+        ctl_counts.append(len(rows))
+        ctl_ratios.extend(ratios.tolist())
+    ctl_ratios = np.array(ctl_ratios)
+    assert min(ctl_counts) >= 1, "the control shows no re-association noise: fixture broken?"
+    # the strict 1 + 1e-5 criterion is violated by the reference itself:
+    assert (ctl_ratios > 1.0 + 1e-5).any() and (ctl_ratios < 1.0 - 1e-5).any()
+    q = make_quantizer(D, N, K, p, DEV)
+    ours = q.encode(x.to(DEV)).cpu().numpy().astype(np.int64)
+    rows, ratios = disagreement(ours, ref, x.numpy(), cs)
+    _record("parity_control", "c2_65536", {"ours_differing": int(len(rows)), "control_differing": ctl_counts,
+                                           "ours_ratios": ratios.tolist(), "control_ratios": ctl_ratios.tolist()})
+    assert len(rows) / B <= 1e-4, f"{len(rows)}/{B} frames differ"
+    # (a) no more frequent than 2x the control (mean over the permutations; +2 frames of Poisson slack at these counts)
+    assert len(rows) <= 2 * np.mean(ctl_counts) + 2, (len(rows), ctl_counts)
+    # (b) no wider than the control, and not one-sided: ours better on some frames, worse on others (or too few to tell)
+    assert _width(ratios) <= max(_width(ctl_ratios) * 1.25, 1e-3), (_width(ratios), _width(ctl_ratios))
+    if len(ratios) >= 6:
+        assert (ratios < 1).any() and (ratios > 1).any(), ratios
+
+
+def test_full_size_parity_against_live_reference():
+    """BASELINE config 2 in full (2^20 frames): ours against the unmodified reference (baseline/_ref) run on the same
+    GPU, with the reference's permuted self as the control, 65,536-frame reference sub-batches."""
+    refq = reference_package()
+    if refq is None:
+        pytest.skip("baseline/_ref is not installed (see DESIGN.md 6); the 65,536-frame fixture test covers this")
+    D, N, K, B = 512, 8, 256, 1 << 20
+    p = synth.synth_params(D, N, K, 0)
+    x = synth.synth_x(B, D, 1234 + 1).to(DEV)
+    q = make_quantizer(D, N, K, p, DEV)
+    ours = q.encode(x)
+
+    def ref_codes(params, xin):
+        r = refq.Quantizer(dim=D, codebook_size=K, num_codebooks=N)
+        with torch.no_grad():
+            r.centers.copy_(params["centers"])
+            r.to_logits.weight.copy_(params["weight"])
+            r.to_logits.bias.copy_(params["bias"])
+            r = r.to(DEV)
+            return torch.cat([r.encode(xin[i:i + 32768], refine_indexes_iters=5) for i in range(0, B, 32768)])
+    ref = ref_codes(p, x)
+    perm = torch.randperm(D, generator=torch.Generator().manual_seed(11))
+    pp = dict(centers=p["centers"][:, :, perm].contiguous(), weight=p["weight"][:, perm].contiguous(), bias=p["bias"])
+    ctl = ref_codes(pp, x[:, perm.to(DEV)].contiguous())
+    xs, cs = x.cpu().numpy(), p["centers"].numpy()
+    r_o, ratios_o = disagreement(ours.cpu().numpy().astype(np.int64), ref.cpu().numpy().astype(np.int64), xs, cs)
+    r_c, ratios_c = disagreement(ctl.cpu().numpy().astype(np.int64), ref.cpu().numpy().astype(np.int64), xs, cs)
+    _record("parity_full_size", "c2_1M", {"ours_differing": int(len(r_o)), "control_differing": int(len(r_c)),
+                                          "ours_ratio_min_med_max": [float(np.min(ratios_o)), float(np.median(ratios_o)),
+                                                                     float(np.max(ratios_o))] if len(r_o) else None,
+                                          "control_ratio_min_med_max": [float(np.min(ratios_c)), float(np.median(ratios_c)),
+                                                                        float(np.max(ratios_c))] if len(r_c) else None,
+                                          "ours_better": int((ratios_o < 1).sum()), "ours_worse": int((ratios_o > 1).sum())})
+    assert len(r_o) / B <= 1e-4, f"{len(r_o)}/{B} frames differ from the reference"
+    assert len(r_o) <= 2 * len(r_c) + 10, (len(r_o), len(r_c))
+    assert _width(ratios_o) <= max(_width(ratios_c) * 1.5, 1e-3), (_width(ratios_o), _width(ratios_c))
+    assert abs(float(np.median(np.log(ratios_o)))) <= 5e-3  # symmetric around 1: near-tie noise, not a bias
+    assert (ratios_o < 1).sum() >= len(ratios_o) * 0.25 and (ratios_o > 1).sum() >= len(ratios_o) * 0.25
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Trainer end quality against a reference-trained run (reference's own yardstick, test_quantization.py:11-48, 51-84)
+
+@pytest.mark.parametrize("kind", ["mlp", "gauss"])
+def test_trainer_quality_parity(kind):
+    g, m = load_npz("golden_trainer_quality.npz")
+    dim, B = m["dim"], m["B"]
+    torch.manual_seed(1)
+    random.seed(1)
+    gen_x = trainer_quality_data(kind, dim)
+    tr = QuantizerTrainer(dim=dim, bytes_per_frame=m["bytes_per_frame"], device=DEV,
+                          phase_one_iters=m["phase_one_iters"], phase_two_iters=m["phase_two_iters"])
+    while not tr.done():
+        tr.step(gen_x(B).to(DEV))
+    q = tr.get_quantizer()
+    assert (q.codebook_size, q.num_codebooks) == (256, m["bytes_per_frame"])
+    x_mean = q.get_data_mean()
+    errs = []
+    with torch.no_grad():
+        for _ in range(m["eval_batches"]):
+            x = gen_x(B).to(DEV)
+            xa = q.decode(q.encode(x))
+            errs.append(float(((x - xa) ** 2).sum() / ((x - x_mean) ** 2).sum()))
+    ours, ref = float(np.mean(errs)), m[f"{kind}_avg_rel_err"]
+    _record("trainer_quality", kind, {"ours": ours, "reference": ref, "shannon": m["shannon_distortion"]})
+    # SURVEY section 7 hard part 5: final relative error of the two implementations within ~1-2 % of each other
+    assert abs(ours - ref) <= 0.02 * ref, (ours, ref)
+    if kind == "gauss":  # same distance from the Shannon bound (test_quantization.py:55-60)
+        sh = m["shannon_distortion"]
+        assert ours >= sh * 0.999, (ours, sh)
+        assert abs((ours - sh) - (ref - sh)) <= 0.25 * (ref - sh) + 0.005, (ours, ref, sh)
+
+
+def test_reference_trained_dim256_quantizer_codes():
+    """The 4 x 256 quantizer the reference trained at dim 256 (golden_trainer_quality.npz) loaded into ours: codes of
+    2,048 fresh frames equal the reference's, or differ only on adjudicated fp32 near-ties."""
+    g, m = load_npz("golden_trainer_quality.npz")
+    sd = {k[len("mlp/state/"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("mlp/state/")}
+    q = Quantizer(dim=m["dim"], codebook_size=256, num_codebooks=m["bytes_per_frame"])
+    q.load_state_dict(sd)
+    q = q.to(DEV)
+    x = torch.from_numpy(g["mlp/x_eval"])
+    ours = q.encode(x.to(DEV)).cpu().numpy().astype(np.int64)
+    ref = g["mlp/codes"].astype(np.int64)
+    with torch.no_grad():
+        cs = q.get_centers().cpu().numpy()
+    rows, ratios = disagreement(ours, ref, x.numpy(), cs)
+    assert len(rows) <= 1, f"{len(rows)}/2048 frames differ"
+    if len(rows):
+        _, margin = oracle.compute_indexes(x.numpy()[rows], sd["centers"].numpy(), sd["to_logits.weight"].numpy(),
+                                           sd["to_logits.bias"].numpy(), float(sd["centers_scale"]),
+                                           float(sd["logits_scale"]), iters=5, return_margin=True)
+        assert np.all(margin <= 1e-6) and _width(ratios) <= 0.1, (margin, ratios)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Regressions from the round-1 review
+
+def test_trainer_graph_and_eager_steps_interleave():
+    """after a CUDA-graph capture / replay `p.grad` pointed at the graph's buffers, and the next EAGER step
+    (diagnostics iteration, warm-up of the other pass count) accumulated onto the previous replay's gradients.  Runs
+    graphed and eager trainers side by side with two_iter_prob = 0.5 across two diagnostics iterations."""
+    dim, B = 64, 512
+    xs = [synth.synth_x(B, dim, 900 + i).to(DEV) for i in range(8)]
+
+    def run(use_graph):
+        torch.manual_seed(3)
+        random.seed(3)
+        tr = QuantizerTrainer(dim=dim, bytes_per_frame=2, device=DEV, phase_one_iters=10000, phase_two_iters=10000)
+        tr._use_graph = use_graph
+        tr.cur_iter = 170  # 30 steps up to the diagnostics iteration 200, then on to 230
+        for i in range(60):
+            tr.step(xs[i % len(xs)])
+            assert all(p.grad is None for p in tr.quantizer.parameters())
+        return tr, {k: v.detach().clone() for k, v in tr.quantizer.state_dict().items()}
+    tg, a = run(True)
+    assert len(tg._graphs) >= 1, "no CUDA graph was captured: the test would not exercise the replay path"
+    _, b = run(False)
+    for k in a:
+        if a[k].dtype.is_floating_point:
+            assert torch.allclose(a[k], b[k], rtol=2e-3, atol=2e-5), (k, (a[k] - b[k]).abs().max())
+
+
+_TAIL_CHUNK_SCRIPT = r"""
+import os, sys, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+from quantization_b200 import synth
+from helpers import make_quantizer
+dev = torch.device("cuda:0")
+D, N, K = 64, 4, 256
+B = 148 * 128 + 1000          # one full 18,944-frame chunk (MCQ_CHUNK_WAVES=1) + a tail that is not a multiple of it
+p = synth.synth_params(D, N, K, 5)
+x = synth.synth_x(B, D, 31).to(dev)
+def losses(gemm):
+    os.environ["MCQ_GEMM"] = gemm
+    q = make_quantizer(D, N, K, p, dev)
+    out = q.compute_loss(x, 1)
+    (out[1] + out[2]).backward()
+    return [float(v) for v in out], q.to_logits.weight.grad.clone(), q.to_logits.bias.grad.clone()
+a, gwa, gba = losses("tc")
+b, gwb, gbb = losses("ffma")
+print("LOSSES", a, b)
+assert all(abs(u - v) <= 2e-6 * max(1.0, abs(v)) for u, v in zip(a, b)), (a, b)
+assert torch.allclose(gwa, gwb, rtol=1e-3, atol=1e-7) and torch.allclose(gba, gbb, rtol=1e-3, atol=1e-7)
+print("TAIL_OK")
+"""
+
+
+def test_class_loss_tail_chunk_uses_the_right_split_plane():
+    """in the last (shorter) chunk of a batch larger than one chunk the classifier GEMM read its second fp16
+    plane at the wrong row offset (logits accurate to ~2^-11 only).  The chunk size is fixed per process, hence the
+    subprocess with MCQ_CHUNK_WAVES=1; the tcgen05 path must agree with the CUDA-core fp32 GEMM to fp32 accuracy."""
+    env = dict(os.environ, MCQ_CHUNK_WAVES="1")
+    r = subprocess.run([sys.executable, "-c", _TAIL_CHUNK_SCRIPT.format(root=_ROOT)], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "TAIL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_product_quantizer_and_correlations_match_reference():
+    """get_product_quantizer (quantization.py:81-112) and compute_codebook_correlations (:150-181) against
+    outputs of the reference itself (golden_misc.npz), on the device."""
+    g, meta = load_npz("golden_misc.npz")
+    for name, m in meta.items():
+        p = synth.synth_params(m["D"], m["N"], m["K"], m["seed"])
+        q = make_quantizer(m["D"], m["N"], m["K"], p, DEV, m["centers_scale"], m["logits_scale"])
+        corr = q.compute_codebook_correlations().cpu().numpy()
+        ref = g[f"{name}/correlations"]
+        assert corr.shape == ref.shape and np.allclose(corr, ref, rtol=2e-4, atol=2e-6), np.abs(corr - ref).max()
+        if m["K"] == 16:
+            pq = q.get_product_quantizer()
+            assert (pq.codebook_size, pq.num_codebooks) == (256, m["N"] // 2)
+            for what, t in (("weight", pq.to_logits.weight), ("bias", pq.to_logits.bias), ("centers", pq.centers)):
+                assert synth.sha256_of(t) == bytes(g[f"{name}/pq_{what}_sha"]).decode(), (name, what)
+            assert np.allclose([float(pq.logits_scale), float(pq.centers_scale)], g[f"{name}/pq_scales"])
+            x = synth.synth_x(256, m["D"], 77).to(DEV)
+            codes = pq.encode(x, refine_indexes_iters=2).cpu().numpy()
+            assert int((codes != g[f"{name}/pq_codes"]).any(1).sum()) == 0
+
+
+def test_search_stats_count_executed_passes():
+    """mcq_search_stats: the counters the roofline accounting reads (passes actually executed <= passes requested)."""
+    D, N, K, B = 256, 8, 256, 4096
+    p = synth.synth_params(D, N, K, 0)
+    q = make_quantizer(D, N, K, p, DEV)
+    x = synth.synth_x(B, D, 5).to(DEV)
+    q.encode(x)
+    ws = q._workspace(B)
+    _lib.search_stats(ws, reset=True, read=False)
+    q.encode(x, refine_indexes_iters=5)
+    passes, frames = _lib.search_stats(ws)
+    assert frames == B and 2 * B <= passes <= 5 * B, (passes, frames)
+    _lib.search_stats(ws, reset=True, read=False)
+    q.encode(x, refine_indexes_iters=1)
+    assert _lib.search_stats(ws, reset=True) == (B, B)
+    assert _lib.search_stats(ws) == (0, 0)

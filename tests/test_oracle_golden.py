@@ -65,9 +65,14 @@ def test_oracle_matches_reference_trained(golden_trained, tag):
                                  p["centers_scale"], p["logits_scale"], iters=5)
     ref = gt[f"{tag}/idx"].astype(np.int64)
     nbad = int((idx != ref).any(1).sum())
-    # The trained state has non-trivial scale parameters; torch's vectorised fp32 exp may differ from the
-    # oracle's correctly rounded exp by an ulp, so allow the fp32 noise floor here.
-    assert nbad <= 2, f"{nbad} of {len(ref)} frames differ"
+    # non-trivial scale parameters: the oracle's correctly rounded exp equals torch's fp32 exp on these values
+    # (checked below), so the codes must be identical
+    for nm in ("centers_scale", "logits_scale"):
+        import math
+        import torch
+        t = float((torch.tensor(p[nm], dtype=torch.float32) * 10.0).exp())
+        assert t == float(np.float32(math.exp(float(np.float32(np.float32(p[nm]) * np.float32(10.0))))))
+    assert nbad == 0, f"{nbad} of {len(ref)} frames differ"
     K = p["centers"].shape[1]
     dec = oracle.decode(gt[f"{tag}/codes"], p["centers"].numpy(), p["centers_scale"])
     head = gt[f"{tag}/decode_head"]

@@ -31,6 +31,11 @@ ws = q._workspace(B)
 _lib.check(L.mcq_xct(x.data_ptr(), 0, B, D, N, K, base, P.data_ptr(), ws.data_ptr(), ws.numel(),
                      _lib.stream_ptr(dev)), "xct")
 idx0 = q.encode(x, refine_indexes_iters=0, as_bytes=False).to(torch.int32).contiguous()
+# refinement passes these frames actually execute (converged frames stop early): counted by the kernels themselves
+_lib.search_stats(ws, reset=True, read=False)
+q.encode(x)
+passes, nfr = _lib.search_stats(ws)
+print(f"frame_passes {passes} frames {nfr} passes_per_frame {passes / max(nfr, 1):.4f}", flush=True)
 VERS = tuple(os.environ.get("MCQ_ONLY", "v1,v2").split(","))
 res = {}
 for ver in VERS:
