@@ -29,6 +29,11 @@ constexpr int K2 = 256;
 #define MCQ_POP_UNROLL 4  // the pop loop is the bulk of the code; full unrolling costs instruction-cache misses
 #endif
 constexpr int POP_UNROLL = MCQ_POP_UNROLL;
+// Interleave the pop chains of two merges of the same level (needs a second list region: +2.8 KB of shared memory per
+// warp).  0 = one merge at a time.
+#ifndef MCQ_MERGE_PAIR
+#define MCQ_MERGE_PAIR 1
+#endif
 // Launch shape: ONE CTA of 16 warps per SM (128 registers per thread).  Measured at C2 (75,776 frames, static striding):
 // 4 CTAs x 5 warps (96 regs) 5.59 ms, 2 x 8 (128 regs) 5.12 ms, 1 x 20 (96 regs) 5.40 ms, 1 x 12 (152 regs) 5.23 ms,
 // 1 x 16 (128 regs) 4.90 ms: fewer, fatter warps win (no spills, and the shared memory one CTA does not take stays L1).
@@ -88,15 +93,25 @@ struct alignas(16) WarpMem2 {
     static constexpr int NG2 = (N >= 2) ? N / 2 : 1;  // groups after the first merge
     static constexpr int NG3 = (N >= 4) ? N / 4 : 1;  // groups after the second merge
     union {
-        float2 lists[9][32];  // per-lane sorted columns (key, flat) + one row of +inf sentinels
+        float2 lists[9][32];  // per-lane sorted columns (key, flat) + one row of sentinels (list_sentinel)
         float es[32][TSTR];   // quad merge: E_b[i][q]  (overwrites the sentinel row; restored after the merge)
     };
-    float tab[TAB_FLOATS];   // level-1 scratch (v of the 256 candidates); T_ab of the quad merge (trow_off)
+#if MCQ_MERGE_PAIR
+    union {
+        float tab[TAB_FLOATS];   // T_ab of the quad merge (trow_off)
+        float2 lists2[10][32];   // second column set of the interleaved merge selections (merge1_pair, merge2_pair)
+    };
+#else
+    float tab[TAB_FLOATS];   // T_ab of the quad merge (trow_off)
+#endif
     float kd1[N][16];        // level-1 kept candidates of each codebook: delta ...
     int kk[N][16];           // ... and codebook entry k
     unsigned rowk[N][16];    // (n*K + kk[n][p]) * NK: element offset of the G row of each kept candidate
     float uv[N][N][16];      // uv[a][m][p] = G[(m,old_m), (a, kk_a[p])]
     float2 sel[32];          // result of the current selection: (key, flat), ascending
+#if MCQ_MERGE_PAIR
+    float2 sel2[32];         // result of the second of two interleaved merge selections
+#endif
     float kd2[NG2][16];      // kept deltas / slot tuples after the first merge
     unsigned kt2[NG2][16];
     float kd3[NG3][32];      // ... after the second merge
@@ -106,12 +121,44 @@ struct alignas(16) WarpMem2 {
     unsigned used[8];        // quad merge: which level-1 slots of each codebook the 32+32 candidates still use
 };
 
-// The R smallest of the warp's 256 candidates (8 per lane; candidate t of a lane has flat index flat[t], ascending in
-// t), ascending by (key, flat), written to s.sel[0..R).  quantization.py:474-487 (sort + keep the first K_cutoff).
+// Sentinel below the 8 entries of a lane's column: NaN.  redux.sync.min.f32 ignores NaN inputs (the result is NaN only
+// when every lane's head is the sentinel) and `head == min` is false for it, so an exhausted lane never pops again and
+// its column pointer never leaves the list (row 9, the prefetched successor of the sentinel, is still inside the union).
+__device__ __forceinline__ float2 list_sentinel() { return make_float2(__int_as_float(0x7fc00000), __int_as_float(0)); }
+
+// ---- sorted top-R of the warp's 256 candidates ------------------------------------------------------------------------
+// Every lane rank-sorts its 8 keys into its own shared-memory column (s.lists, row 8 = NaN sentinels); R "pops" then
+// take the global minimum from the column heads.  The contract orders candidates by (key, flat index).
+//
+// Fast path (one warp reduction per pop): the lane whose head EQUALS the minimum pops.  That is the contract's order
+// unless two lanes hold bit-equal keys at the same time (then both pop in one step).  Such a step is not looked for
+// while popping -- after the loop the number of popped candidates is summed over the warp, and if it is not exactly R
+// (a tie somewhere, or NaN keys, which never pop) the selection is redone by the exact loop below, which breaks ties
+// with a second reduction over the flat indexes.  Measured: exact ties occur on degenerate inputs only (all-zero
+// frames, duplicated codebook rows); the profile of the two-reduction loop had 39 % of the kernel's stall samples.
 template <class Mem, int R>
-__device__ __forceinline__ void select_sorted(Mem &s, const float (&key)[8], const int (&flat)[8], int lane) {
-    // rank of key[t] among the lane's 8 keys, equal keys in index order:
-    //   rank[t] = #{u < t: key[u] <= key[t]} + #{u > t: key[u] < key[t]}
+__device__ __noinline__ void pops_exact(Mem &s, float2 (*lists)[32], float2 *sel, int lane) {
+    const float2 *col = &lists[0][lane];
+    float2 head = col[0], nxt = col[32];
+#pragma unroll 1
+    for (int r = 0; r < R; ++r) {
+        const float m = credux_min(head.x);
+        // among the lanes holding the minimum the lowest flat index wins (contract: ascending (key, flat))
+        const unsigned f = (head.x == m) ? (unsigned)__float_as_int(head.y) : 0x7fffffffu;
+        const bool mine = (f == __reduce_min_sync(FULL, f)) && f != 0x7fffffffu;
+        if (mine) {
+            sel[r] = head;
+            head = nxt;
+            col += 32;
+            nxt = col[32];  // at most row 9: inside the union (es) even after the sentinel row
+        }
+    }
+    __syncwarp();
+}
+
+// (key[t], flat[t]) of a lane -> its column of `lists`, ascending by (key, t):
+//   rank[t] = #{u < t: key[u] <= key[t]} + #{u > t: key[u] < key[t]}
+__device__ __forceinline__ void rank_sort_store(float2 (*lists)[32], const float (&key)[8], const int (&flat)[8], int lane) {
     int rank[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) rank[t] = 7 - t;
@@ -124,74 +171,67 @@ __device__ __forceinline__ void select_sorted(Mem &s, const float (&key)[8], con
             rank[u] += c;
         }
 #pragma unroll
-    for (int t = 0; t < 8; ++t) s.lists[rank[t]][lane] = make_float2(key[t], __int_as_float(flat[t]));
+    for (int t = 0; t < 8; ++t) lists[rank[t]][lane] = make_float2(key[t], __int_as_float(flat[t]));
+}
+
+// The R smallest of the warp's 256 candidates (8 per lane; candidate t of a lane has flat index flat[t], ascending in
+// t), ascending by (key, flat), written to s.sel[0..R).  quantization.py:474-487 (sort + keep the first K_cutoff).
+template <class Mem, int R>
+__device__ __forceinline__ void select_sorted(Mem &s, const float (&key)[8], const int (&flat)[8], int lane) {
+    rank_sort_store(s.lists, key, flat, lane);
     // a lane reads back only its own column: no warp synchronisation needed here
-    const float2 *col = &s.lists[0][lane];
+    const float2 *col0 = &s.lists[0][lane];
+    const float2 *col = col0;
     float2 head = col[0], nxt = col[32];  // the successor is fetched ahead so that a pop does not wait on shared memory
 #pragma unroll(POP_UNROLL)
     for (int r = 0; r < R; ++r) {
         const float m = credux_min(head.x);
-        // among the lanes holding the minimum the lowest flat index wins (contract: ascending (key, flat))
-        const unsigned f = (head.x == m) ? (unsigned)__float_as_int(head.y) : 0x7fffffffu;
-        const bool mine = (f == __reduce_min_sync(FULL, f)) && f != 0x7fffffffu;
-        if (mine) {
+        if (head.x == m) {
             s.sel[r] = head;
             head = nxt;
             col += 32;
             nxt = col[32];  // at most row 9: inside the union (es) even after the sentinel row
         }
     }
+    const int popped = (int)(col - col0) >> 5;
+    if (__reduce_add_sync(FULL, popped) != R) pops_exact<Mem, R>(s, s.lists, s.sel, lane);
     __syncwarp();
 }
 
 // Two independent selections at once (same flat numbering): the two pop chains are interleaved, so the latency of one
-// chain's warp reductions is covered by the other's.  The second selection uses caller-supplied memory: `lists2` (10 rows
-// of 32 float2; row 8 gets the +inf sentinels here, row 9 is only ever prefetched) and `sel2` (R entries).
+// chain's warp reduction is covered by the other's.  The second selection uses caller-supplied memory: `lists2` (10 rows
+// of 32 float2; row 8 gets the sentinels here, row 9 is only ever prefetched) and `sel2` (R entries).
 template <class Mem, int R>
 __device__ __forceinline__ void select_sorted2(Mem &s, const float (&keyA)[8], const float (&keyB)[8],
                                                const int (&flat)[8], int lane, float2 (*lists2)[32], float2 *sel2) {
-    int rankA[8], rankB[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) rankA[t] = rankB[t] = 7 - t;
-#pragma unroll
-    for (int t = 1; t < 8; ++t)
-#pragma unroll
-        for (int u = 0; u < t; ++u) {
-            const int ca = le_mask(keyA[u], keyA[t]), cb = le_mask(keyB[u], keyB[t]);
-            rankA[t] -= ca;
-            rankA[u] += ca;
-            rankB[t] -= cb;
-            rankB[u] += cb;
-        }
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        s.lists[rankA[t]][lane] = make_float2(keyA[t], __int_as_float(flat[t]));
-        lists2[rankB[t]][lane] = make_float2(keyB[t], __int_as_float(flat[t]));
-    }
-    lists2[8][lane] = make_float2(__int_as_float(0x7f800000), __int_as_float(0));
-    const float2 *colA = &s.lists[0][lane], *colB = &lists2[0][lane];
+    rank_sort_store(s.lists, keyA, flat, lane);
+    rank_sort_store(lists2, keyB, flat, lane);
+    lists2[8][lane] = list_sentinel();
+    const float2 *colA0 = &s.lists[0][lane], *colB0 = &lists2[0][lane];
+    const float2 *colA = colA0, *colB = colB0;
     float2 headA = colA[0], nxtA = colA[32], headB = colB[0], nxtB = colB[32];
 #pragma unroll(POP_UNROLL)
     for (int r = 0; r < R; ++r) {
         const float mA = credux_min(headA.x);
         const float mB = credux_min(headB.x);
-        const unsigned fA = (headA.x == mA) ? (unsigned)__float_as_int(headA.y) : 0x7fffffffu;
-        const unsigned fB = (headB.x == mB) ? (unsigned)__float_as_int(headB.y) : 0x7fffffffu;
-        const unsigned wA = __reduce_min_sync(FULL, fA);
-        const unsigned wB = __reduce_min_sync(FULL, fB);
-        if (fA == wA && fA != 0x7fffffffu) {
+        if (headA.x == mA) {
             s.sel[r] = headA;
             headA = nxtA;
             colA += 32;
             nxtA = colA[32];
         }
-        if (fB == wB && fB != 0x7fffffffu) {
+        if (headB.x == mB) {
             sel2[r] = headB;
             headB = nxtB;
             colB += 32;
             nxtB = colB[32];
         }
     }
+    // both chains in one reduction: A's count in the low half, B's in the high half
+    const int popped = ((int)(colA - colA0) >> 5) + (((int)(colB - colB0) >> 5) << 16);
+    const int tot = __reduce_add_sync(FULL, popped);
+    if ((tot & 0xffff) != R) pops_exact<Mem, R>(s, s.lists, s.sel, lane);
+    if ((tot >> 16) != R) pops_exact<Mem, R>(s, lists2, sel2, lane);
     __syncwarp();
 }
 
@@ -326,8 +366,8 @@ __device__ __forceinline__ void gather_uv(WarpMem2<N> &s, const float *__restric
 
 // Merge of two single codebooks e = 2g, o = 2g+1: 16 x 16 joint candidates (quantization.py:504-547 at L = 1).
 // Lane (hi, j) scores candidates (i = 8*hi + t, j), t = 0..7: a request reads two G rows x 16 columns.
-template <int N, bool FINAL>
-__device__ __forceinline__ void merge1(WarpMem2<N> &s, const float *__restrict__ G, int g, int lane) {
+template <int N>
+__device__ __forceinline__ void merge1_keys(WarpMem2<N> &s, const float *__restrict__ G, int g, int lane, float (&key)[8]) {
     const int e = 2 * g, o = e + 1;
     const int j = lane & 15, ib = (lane >> 4) * 8;
     const unsigned ko = o * K2 + s.kk[o][j];
@@ -351,14 +391,37 @@ __device__ __forceinline__ void merge1(WarpMem2<N> &s, const float *__restrict__
     float gv[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) gv[t] = gat(G, rowp[t] + ko);
-    float key[8];
-    int flat[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
         const float d = ((gv[t] - u[t]) - v) + w;
         key[t] = fmaf(2.0f, d, kde[t] + kdo);
-        flat[t] = (ib + t) * 16 + j;
     }
+}
+
+// flat index of the joint candidate (i = 8*hi + t, j) a lane scores in merge1 / merge2: i * 16 + j
+__device__ __forceinline__ void merge_flat(int lane, int (&flat)[8]) {
+    const int j = lane & 15, ib = (lane >> 4) * 8;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) flat[t] = (ib + t) * 16 + j;
+}
+
+template <int N>
+__device__ __forceinline__ void merge1_store(WarpMem2<N> &s, int g, int lane, const float2 *sel) {
+    if (lane < 16) {
+        const float2 r = sel[lane];
+        const int fl = __float_as_int(r.y);
+        s.kd2[g][lane] = r.x;
+        s.kt2[g][lane] = (unsigned)(fl >> 4) | ((unsigned)(fl & 15) << 4);
+    }
+}
+
+template <int N, bool FINAL>
+__device__ __forceinline__ void merge1(WarpMem2<N> &s, const float *__restrict__ G, int g, int lane) {
+    const int e = 2 * g, o = e + 1;
+    float key[8];
+    int flat[8];
+    merge1_keys<N>(s, G, g, lane, key);
+    merge_flat(lane, flat);
     if constexpr (FINAL) {
         const int fl = select_best(key, flat, lane);
         __syncwarp();  // every lane has read old[] (above) before lane 0 overwrites it
@@ -370,20 +433,29 @@ __device__ __forceinline__ void merge1(WarpMem2<N> &s, const float *__restrict__
         __syncwarp();
     } else {
         select_sorted<WarpMem2<N>, 16>(s, key, flat, lane);
-        if (lane < 16) {
-            const float2 r = s.sel[lane];
-            const int fl = __float_as_int(r.y);
-            s.kd2[g][lane] = r.x;
-            s.kt2[g][lane] = (unsigned)(fl >> 4) | ((unsigned)(fl & 15) << 4);
-        }
+        merge1_store<N>(s, g, lane, s.sel);
         __syncwarp();
     }
 }
 
+// Two merges of single codebooks (g, g + 1) with interleaved pop chains (like the level-1 pairs).
+template <int N>
+__device__ __forceinline__ void merge1_pair(WarpMem2<N> &s, const float *__restrict__ G, int g, int lane) {
+    float keyA[8], keyB[8];
+    int flat[8];
+    merge1_keys<N>(s, G, g, lane, keyA);
+    merge1_keys<N>(s, G, g + 1, lane, keyB);
+    merge_flat(lane, flat);
+    select_sorted2<WarpMem2<N>, 16>(s, keyA, keyB, flat, lane, s.lists2, s.sel2);
+    merge1_store<N>(s, g, lane, s.sel);
+    merge1_store<N>(s, g + 1, lane, s.sel2);
+    __syncwarp();
+}
+
 // Merge of two codebook pairs: groups e = 2g (codebooks 4g, 4g+1) and o = 2g+1 (4g+2, 4g+3), 16 x 16 candidates.
 // Same lane mapping as merge1: lane (hi, j) scores (i = 8*hi + t, j).
-template <int N, bool FINAL>
-__device__ __forceinline__ void merge2(WarpMem2<N> &s, const float *__restrict__ G, int g, int lane) {
+template <int N>
+__device__ __forceinline__ void merge2_keys(WarpMem2<N> &s, const float *__restrict__ G, int g, int lane, float (&key)[8]) {
     const int e = 2 * g, o = e + 1;
     const int a0 = 4 * g, a1 = a0 + 1, b0 = a0 + 2, b1 = a0 + 3;
     const int j = lane & 15, ib = (lane >> 4) * 8;
@@ -415,8 +487,6 @@ __device__ __forceinline__ void merge2(WarpMem2<N> &s, const float *__restrict__
         g01[t] = gat(G, rp0 + c1);
         g11[t] = gat(G, rp1 + c1);
     }
-    float key[8];
-    int flat[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
         const int ia0 = tis[t] & 15, ia1 = tis[t] >> 4;
@@ -427,8 +497,26 @@ __device__ __forceinline__ void merge2(WarpMem2<N> &s, const float *__restrict__
         const float wb0 = d00 + d10, wb1 = d01 + d11;  // inner sums over a, then b ascending
         const float dot = wb0 + wb1;
         key[t] = fmaf(2.0f, dot, kde[t] + kdo);
-        flat[t] = (ib + t) * 16 + j;
     }
+}
+
+template <int N>
+__device__ __forceinline__ void merge2_store(WarpMem2<N> &s, int g, int lane, const float2 *sel) {
+    const int e = 2 * g, o = e + 1;
+    const float2 r = sel[lane];
+    const int fl = __float_as_int(r.y);
+    s.kd3[g][lane] = r.x;
+    s.kt3[g][lane] = s.kt2[e][fl >> 4] | (s.kt2[o][fl & 15] << 8);
+}
+
+template <int N, bool FINAL>
+__device__ __forceinline__ void merge2(WarpMem2<N> &s, const float *__restrict__ G, int g, int lane) {
+    const int e = 2 * g, o = e + 1;
+    const int a0 = 4 * g, a1 = a0 + 1, b0 = a0 + 2, b1 = a0 + 3;
+    float key[8];
+    int flat[8];
+    merge2_keys<N>(s, G, g, lane, key);
+    merge_flat(lane, flat);
     if constexpr (FINAL) {
         const int fl = select_best(key, flat, lane);
         __syncwarp();  // every lane has read old[] (above) before lane 0 overwrites it
@@ -444,14 +532,23 @@ __device__ __forceinline__ void merge2(WarpMem2<N> &s, const float *__restrict__
         __syncwarp();
     } else {
         select_sorted<WarpMem2<N>, 32>(s, key, flat, lane);
-        {
-            const float2 r = s.sel[lane];
-            const int fl = __float_as_int(r.y);
-            s.kd3[g][lane] = r.x;
-            s.kt3[g][lane] = s.kt2[e][fl >> 4] | (s.kt2[o][fl & 15] << 8);
-        }
+        merge2_store<N>(s, g, lane, s.sel);
         __syncwarp();
     }
+}
+
+// The two merges of codebook pairs of N = 8 (g = 0, 1) with interleaved pop chains.
+template <int N>
+__device__ __forceinline__ void merge2_pair(WarpMem2<N> &s, const float *__restrict__ G, int g, int lane) {
+    float keyA[8], keyB[8];
+    int flat[8];
+    merge2_keys<N>(s, G, g, lane, keyA);
+    merge2_keys<N>(s, G, g + 1, lane, keyB);
+    merge_flat(lane, flat);
+    select_sorted2<WarpMem2<N>, 32>(s, keyA, keyB, flat, lane, s.lists2, s.sel2);
+    merge2_store<N>(s, g, lane, s.sel);
+    merge2_store<N>(s, g + 1, lane, s.sel2);
+    __syncwarp();
 }
 
 // Final merge of two codebook quads (N = 8): 32 x 32 joint candidates, candidate flat = i*32 + j.
@@ -538,7 +635,7 @@ __device__ __forceinline__ void merge4_final(WarpMem2<N> &s, const float *__rest
         for (int i = 0; i < 32; ++i) dot[i] = dot[i] + s.es[i][jq];
         __syncwarp();
     }
-    s.lists[8][lane] = make_float2(__int_as_float(0x7f800000), __int_as_float(0));  // es overwrote the sentinels
+    s.lists[8][lane] = list_sentinel();  // es overwrote the sentinels
     const float kdo = s.kd3[1][lane];
     float best = fmaf(2.0f, dot[0], s.kd3[0][0] + kdo);
     int bi = 0;
@@ -571,13 +668,22 @@ __device__ __forceinline__ void refine_pass2(WarpMem2<N> &s, const float *__rest
     if constexpr (N == 2) {
         merge1<N, true>(s, G, 0, lane);
     } else {
+#if MCQ_MERGE_PAIR
+#pragma unroll 1
+        for (int g = 0; g < N / 2; g += 2) merge1_pair<N>(s, G, g, lane);
+#else
 #pragma unroll 1
         for (int g = 0; g < N / 2; ++g) merge1<N, false>(s, G, g, lane);
+#endif
         if constexpr (N == 4) {
             merge2<N, true>(s, G, 0, lane);
         } else {
+#if MCQ_MERGE_PAIR
+            merge2_pair<N>(s, G, 0, lane);
+#else
 #pragma unroll 1
             for (int g = 0; g < N / 4; ++g) merge2<N, false>(s, G, g, lane);
+#endif
             merge4_final<N>(s, G, lane);
         }
     }
@@ -796,7 +902,7 @@ __device__ __forceinline__ void wide_dots(WarpMem16 &s, const float *__restrict_
         for (int i = 0; i < 32; ++i) dot[i] = dot[i] + s.es[i][jq];
         __syncwarp();
     }
-    s.lists[8][lane] = make_float2(__int_as_float(0x7f800000), __int_as_float(0));  // es overwrote the sentinels
+    s.lists[8][lane] = list_sentinel();  // es overwrote the sentinels
     __syncwarp();
 }
 
@@ -899,7 +1005,7 @@ __global__ void __launch_bounds__(WPC16 * 32, MCQ_S16_MINB)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpMem16 &s = reinterpret_cast<WarpMem16 *>(smem_raw)[warp];
-    s.lists[8][lane] = make_float2(__int_as_float(0x7f800000), __int_as_float(0));
+    s.lists[8][lane] = list_sentinel();
     s.sel[lane] = make_float2(0.0f, __int_as_float(0));
     __syncwarp();
     const int64_t nwarps = (int64_t)gridDim.x * WPC16;
@@ -966,7 +1072,7 @@ __global__ void __launch_bounds__(Launch2<N>::WPC * 32, Launch2<N>::MINB)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int wpc = Launch2<N>::WPC;
     WarpMem2<N> &s = reinterpret_cast<WarpMem2<N> *>(smem_raw)[warp];
-    s.lists[8][lane] = make_float2(__int_as_float(0x7f800000), __int_as_float(0));
+    s.lists[8][lane] = list_sentinel();
     s.sel[lane] = make_float2(0.0f, __int_as_float(0));
     __syncwarp();
     // the first frame of a warp is its global warp index; further frames come from the work counter when there is

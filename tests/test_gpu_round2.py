@@ -175,27 +175,51 @@ def test_reference_trained_dim256_quantizer_codes():
 
 def test_trainer_graph_and_eager_steps_interleave():
     """after a CUDA-graph capture / replay `p.grad` pointed at the graph's buffers, and the next EAGER step
-    (diagnostics iteration, warm-up of the other pass count) accumulated onto the previous replay's gradients.  Runs
-    graphed and eager trainers side by side with two_iter_prob = 0.5 across two diagnostics iterations."""
-    dim, B = 64, 512
-    xs = [synth.synth_x(B, dim, 900 + i).to(DEV) for i in range(8)]
+    (diagnostics iteration, warm-up of the other pass count) accumulated onto the previous replay's gradients.
+    (i) invariant, with two_iter_prob = 0.5 across a diagnostics iteration: every update that is launched eagerly
+    starts with no gradient on any parameter, and none is left behind after any step; (ii) numbers, with one pass count:
+    a graphed and an eager trainer stay together step by step THROUGH the eager diagnostics step that follows replays
+    (training on discrete codes amplifies rounding differences, so the comparison runs over 14 steps, like
+    test_trainer_cuda_graph_equals_eager; a doubled gradient at the diagnostics step shows as ~2e-3)."""
+    dim, B = 64, 2048
+    xs = [synth.synth_x(B, dim, 900 + i).to(DEV) for i in range(4)]
 
-    def run(use_graph):
+    def make(use_graph, prob):
         torch.manual_seed(3)
         random.seed(3)
         tr = QuantizerTrainer(dim=dim, bytes_per_frame=2, device=DEV, phase_one_iters=10000, phase_two_iters=10000)
         tr._use_graph = use_graph
-        tr.cur_iter = 170  # 30 steps up to the diagnostics iteration 200, then on to 230
-        for i in range(60):
-            tr.step(xs[i % len(xs)])
-            assert all(p.grad is None for p in tr.quantizer.parameters())
-        return tr, {k: v.detach().clone() for k, v in tr.quantizer.state_dict().items()}
-    tg, a = run(True)
-    assert len(tg._graphs) >= 1, "no CUDA graph was captured: the test would not exercise the replay path"
-    _, b = run(False)
-    for k in a:
-        if a[k].dtype.is_floating_point:
-            assert torch.allclose(a[k], b[k], rtol=2e-3, atol=2e-5), (k, (a[k] - b[k]).abs().max())
+        tr.two_iter_prob = prob
+        return tr
+    # (i)
+    tr = make(True, 0.5)
+    tr.cur_iter = 170
+    seen = []
+    orig = tr._loss_and_update
+
+    def spy(x, n):
+        seen.append((tr.cur_iter, torch.cuda.is_current_stream_capturing(),
+                     all(p.grad is None for p in tr.quantizer.parameters())))
+        return orig(x, n)
+    tr._loss_and_update = spy
+    for i in range(60):
+        tr.step(xs[i % len(xs)])
+        assert all(p.grad is None for p in tr.quantizer.parameters())
+    assert len(tr._graphs) == 2, "both pass counts should have been captured"
+    assert all(clean for _, _, clean in seen), [s for s in seen if not s[2]]
+    eager_after_capture = [it for it, cap, _ in seen if not cap and it >= 200]
+    assert 200 in eager_after_capture, "the diagnostics step at iteration 200 must have run eagerly after replays"
+    # (ii)
+    eager, graphed = make(False, 0.0), make(True, 0.0)
+    for t in (eager, graphed):
+        t.cur_iter = 190
+    for i in range(14):  # 190..192 eager, 193 capture + replay, ..., 200 eager (diagnostics), 201.. replays
+        for t in (eager, graphed):
+            t.step(xs[i % len(xs)])
+        for (k, a), (_, b) in zip(eager.quantizer.state_dict().items(), graphed.quantizer.state_dict().items()):
+            if a.dtype.is_floating_point:
+                assert (a - b).abs().max().item() <= 1e-4 * (a.abs().max().item() + 1e-6), (i, k)
+    assert len(graphed._graphs) == 1
 
 
 _TAIL_CHUNK_SCRIPT = r"""
