@@ -30,9 +30,10 @@ constexpr int K2 = 256;
 #endif
 constexpr int POP_UNROLL = MCQ_POP_UNROLL;
 // Interleave the pop chains of two merges of the same level (needs a second list region: +2.8 KB of shared memory per
-// warp).  0 = one merge at a time.
+// warp).  0 = one merge at a time.  Measured at C2 (75,776 frames, static striding): 5.17 ms paired vs 4.78 ms one at a
+// time -- the extra shared memory costs more (L1 left for the gathers) than the second chain hides; default off.
 #ifndef MCQ_MERGE_PAIR
-#define MCQ_MERGE_PAIR 1
+#define MCQ_MERGE_PAIR 0
 #endif
 // Launch shape: ONE CTA of 16 warps per SM (128 registers per thread).  Measured at C2 (75,776 frames, static striding):
 // 4 CTAs x 5 warps (96 regs) 5.59 ms, 2 x 8 (128 regs) 5.12 ms, 1 x 20 (96 regs) 5.40 ms, 1 x 12 (152 regs) 5.23 ms,

@@ -206,8 +206,14 @@ class Quantizer(nn.Module):
     def _params(self):
         return (self.centers, self.centers_scale, self.to_logits.weight, self.to_logits.bias, self.logits_scale)
 
+    def invalidate_prepared(self) -> None:
+        """Forget the prepared state.  Needed only after changing parameter VALUES in a way PyTorch's version counters
+        do not see (a fused optimiser step outside compute_loss, writes through raw pointers)."""
+        self._prep_key = None
+
     def _prepared(self) -> Tensor:
-        """The prepared blob (scaled centers, Gram table, operand splits), rebuilt when any parameter changes."""
+        """The prepared blob (scaled centers, Gram table, operand splits), rebuilt when any parameter changes (as seen
+        through data_ptr / _version; compute_loss additionally drops it around every training step)."""
         if self.codebook_size > MAX_CODEBOOK_SIZE or self.num_codebooks > MAX_NUM_CODEBOOKS:
             # e.g. get_product_quantizer() of a codebook_size-256 quantizer: constructible (as in the reference), but
             # there is no kernel for it and no PyTorch fallback by design
@@ -384,6 +390,21 @@ class Quantizer(nn.Module):
         reference defines them (quantization.py:184-242); only the index search and the decode gather run in the
         CUDA library (the search carries no gradient in the reference either)."""
         x = x.reshape(-1, self.dim)
+        # A training step: the parameters have probably just been changed by an optimiser, and fused optimisers
+        # (torch.optim.Adam(fused=True), which QuantizerTrainer uses) do NOT bump the tensors' version counters the
+        # prepared-state cache is keyed on.  So the cache is dropped on entry (this step prepares from the current
+        # values, once) and again on exit (whatever runs after the optimiser step -- the trainer's no_grad
+        # diagnostics, an encode() -- must not see this step's tables).
+        training_call = torch.is_grad_enabled() and any(p.requires_grad for p in self._params())
+        if training_call:
+            self._prep_key = None
+        try:
+            return self._compute_loss(x, refine_indexes_iters)
+        finally:
+            if training_call:
+                self._prep_key = None
+
+    def _compute_loss(self, x: Tensor, refine_indexes_iters: int):
         with torch.no_grad():
             indexes = self._compute_indexes(x, refine_indexes_iters)
         if self.dim <= 1024 and x.shape[0] > 0:

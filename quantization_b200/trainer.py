@@ -89,7 +89,10 @@ class QuantizerTrainer(object):
             graph = torch.cuda.CUDAGraph()
             try:
                 with torch.cuda.graph(graph):
-                    losses = self._loss_and_update(static_x, num_iters)
+                    # detached: the caller only reads the values.  Keeping grad_fn alive would keep the captured
+                    # autograd graph -- and its AccumulateGrad nodes, which are bound to the capture stream -- alive,
+                    # and every later EAGER backward would accumulate on that stream instead of the current one
+                    losses = tuple(l.detach() for l in self._loss_and_update(static_x, num_iters))
             except RuntimeError as e:  # not capturable in this environment: same kernels, launched eagerly from now on
                 logging.warning(f"QuantizerTrainer: CUDA-graph capture failed ({e}); continuing without graphs")
                 self._use_graph = False

@@ -222,6 +222,34 @@ def test_trainer_graph_and_eager_steps_interleave():
     assert len(graphed._graphs) == 1
 
 
+def test_prepared_state_follows_fused_optimizer_steps():
+    """torch.optim.Adam(fused=True) -- what QuantizerTrainer uses -- updates parameters WITHOUT bumping their version
+    counters, which the prepared-state cache (scaled centers, Gram table, operand splits) is keyed on.  Found in round 2:
+    eager trainer steps and the no_grad diagnostics ran on tables up to 200 steps old.  After training steps with a
+    fused optimiser, encode() must equal the encode() of a fresh module holding the same state_dict."""
+    dim, B = 64, 1024
+    torch.manual_seed(11)
+    q = Quantizer(dim=dim, codebook_size=16, num_codebooks=4).to(DEV)
+    opt = torch.optim.Adam(q.parameters(), lr=0.01, fused=True)
+    x = synth.synth_x(B, dim, 77).to(DEV)
+    versions = [p._version for p in q.parameters()]
+    for step in range(6):
+        losses = q.compute_loss(x, 1)
+        (losses[0] + losses[1] + 0.01 * losses[2]).backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        with torch.no_grad():  # like the trainer's diagnostics: right after the optimiser step
+            codes = q.encode(x, refine_indexes_iters=2)
+            rel = float(q.compute_loss(x, 2)[0])
+        fresh = Quantizer(dim=dim, codebook_size=16, num_codebooks=4).to(DEV)
+        fresh.load_state_dict(q.state_dict())
+        with torch.no_grad():
+            assert torch.equal(codes, fresh.encode(x, refine_indexes_iters=2)), f"stale prepared state at step {step}"
+            assert rel == float(fresh.compute_loss(x, 2)[0])
+    if [p._version for p in q.parameters()] != versions:
+        pytest.skip("this PyTorch bumps version counters in fused Adam: the scenario is not reproduced")
+
+
 _TAIL_CHUNK_SCRIPT = r"""
 import os, sys, torch
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
