@@ -157,6 +157,75 @@ __device__ __noinline__ void pops_exact(Mem &s, float2 (*lists)[32], float2 *sel
     __syncwarp();
 }
 
+// One pop step of the fast path in predicated PTX with 32-bit shared-memory addresses: 8 instructions.  (The C++ form
+// of the same statements compiled to 16: 64-bit pointer arithmetic on the generic column pointer and register copies;
+// the pop loops are 256 steps per frame-pass -- profiles/r02_search.md.)
+//   m = min over the warp of the column heads (NaN sentinels ignored); the lane whose head equals m stores it to
+//   sel[r], takes its prefetched successor as the new head and prefetches the entry after that.
+//   hk/hf: head (key, flat), nk/nf: its successor, a: shared address of the head's row in this lane's column (rows are
+//   256 bytes apart), sel_a: shared address of sel[first step of the group], U: step within the group.
+template <int U>
+__device__ __forceinline__ void pop_step(float &hk, float &hf, float &nk, float &nf, unsigned &a, unsigned sel_a) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .f32 m;\n\t"
+        "redux.sync.min.f32 m, %0, 0xffffffff;\n\t"
+        "setp.eq.f32 p, %0, m;\n\t"
+        "@p st.shared.v2.f32 [%5+%6], {%0, %1};\n\t"
+        "@p mov.f32 %0, %2;\n\t"
+        "@p mov.f32 %1, %3;\n\t"
+        "@p ld.shared.v2.f32 {%2, %3}, [%4+512];\n\t"
+        "@p add.u32 %4, %4, 256;\n\t"
+        "}"
+        : "+f"(hk), "+f"(hf), "+f"(nk), "+f"(nf), "+r"(a)
+        : "r"(sel_a), "n"(U * 8)
+        : "memory");
+}
+
+// R pops of one column set; returns the number of entries this lane popped
+template <int R>
+__device__ __forceinline__ int pop_loop(float2 (*lists)[32], float2 *sel, int lane) {
+    static_assert(R % 4 == 0, "pop groups of four");
+    const unsigned a0 = (unsigned)__cvta_generic_to_shared(&lists[0][lane]);
+    unsigned a = a0, sa = (unsigned)__cvta_generic_to_shared(sel);
+    float2 head = lists[0][lane], nxt = lists[1][lane];  // the successor is fetched ahead of the pop that needs it
+#pragma unroll(POP_UNROLL / 4 > 0 ? POP_UNROLL / 4 : 1)
+    for (int r0 = 0; r0 < R; r0 += 4) {
+        pop_step<0>(head.x, head.y, nxt.x, nxt.y, a, sa);
+        pop_step<1>(head.x, head.y, nxt.x, nxt.y, a, sa);
+        pop_step<2>(head.x, head.y, nxt.x, nxt.y, a, sa);
+        pop_step<3>(head.x, head.y, nxt.x, nxt.y, a, sa);
+        sa += 32;
+    }
+    return (int)((a - a0) >> 8);
+}
+
+// two interleaved chains; returns popped(A) + (popped(B) << 16)
+template <int R>
+__device__ __forceinline__ int pop_loop2(float2 (*listsA)[32], float2 *selA, float2 (*listsB)[32], float2 *selB, int lane) {
+    static_assert(R % 4 == 0, "pop groups of four");
+    const unsigned a0 = (unsigned)__cvta_generic_to_shared(&listsA[0][lane]);
+    const unsigned b0 = (unsigned)__cvta_generic_to_shared(&listsB[0][lane]);
+    unsigned a = a0, b = b0;
+    unsigned sa = (unsigned)__cvta_generic_to_shared(selA), sb = (unsigned)__cvta_generic_to_shared(selB);
+    float2 hA = listsA[0][lane], nA = listsA[1][lane], hB = listsB[0][lane], nB = listsB[1][lane];
+#pragma unroll(POP_UNROLL / 4 > 0 ? POP_UNROLL / 4 : 1)
+    for (int r0 = 0; r0 < R; r0 += 4) {
+        pop_step<0>(hA.x, hA.y, nA.x, nA.y, a, sa);
+        pop_step<0>(hB.x, hB.y, nB.x, nB.y, b, sb);
+        pop_step<1>(hA.x, hA.y, nA.x, nA.y, a, sa);
+        pop_step<1>(hB.x, hB.y, nB.x, nB.y, b, sb);
+        pop_step<2>(hA.x, hA.y, nA.x, nA.y, a, sa);
+        pop_step<2>(hB.x, hB.y, nB.x, nB.y, b, sb);
+        pop_step<3>(hA.x, hA.y, nA.x, nA.y, a, sa);
+        pop_step<3>(hB.x, hB.y, nB.x, nB.y, b, sb);
+        sa += 32;
+        sb += 32;
+    }
+    return (int)((a - a0) >> 8) + ((int)((b - b0) >> 8) << 16);
+}
+
 // (key[t], flat[t]) of a lane -> its column of `lists`, ascending by (key, t):
 //   rank[t] = #{u < t: key[u] <= key[t]} + #{u > t: key[u] < key[t]}
 __device__ __forceinline__ void rank_sort_store(float2 (*lists)[32], const float (&key)[8], const int (&flat)[8], int lane) {
@@ -180,21 +249,9 @@ __device__ __forceinline__ void rank_sort_store(float2 (*lists)[32], const float
 template <class Mem, int R>
 __device__ __forceinline__ void select_sorted(Mem &s, const float (&key)[8], const int (&flat)[8], int lane) {
     rank_sort_store(s.lists, key, flat, lane);
-    // a lane reads back only its own column: no warp synchronisation needed here
-    const float2 *col0 = &s.lists[0][lane];
-    const float2 *col = col0;
-    float2 head = col[0], nxt = col[32];  // the successor is fetched ahead so that a pop does not wait on shared memory
-#pragma unroll(POP_UNROLL)
-    for (int r = 0; r < R; ++r) {
-        const float m = credux_min(head.x);
-        if (head.x == m) {
-            s.sel[r] = head;
-            head = nxt;
-            col += 32;
-            nxt = col[32];  // at most row 9: inside the union (es) even after the sentinel row
-        }
-    }
-    const int popped = (int)(col - col0) >> 5;
+    // a lane reads back only its own column: no warp synchronisation needed here.  The prefetch reaches at most row
+    // 9: inside the union (es) even after the sentinel row.
+    const int popped = pop_loop<R>(s.lists, s.sel, lane);
     if (__reduce_add_sync(FULL, popped) != R) pops_exact<Mem, R>(s, s.lists, s.sel, lane);
     __syncwarp();
 }
@@ -208,28 +265,8 @@ __device__ __forceinline__ void select_sorted2(Mem &s, const float (&keyA)[8], c
     rank_sort_store(s.lists, keyA, flat, lane);
     rank_sort_store(lists2, keyB, flat, lane);
     lists2[8][lane] = list_sentinel();
-    const float2 *colA0 = &s.lists[0][lane], *colB0 = &lists2[0][lane];
-    const float2 *colA = colA0, *colB = colB0;
-    float2 headA = colA[0], nxtA = colA[32], headB = colB[0], nxtB = colB[32];
-#pragma unroll(POP_UNROLL)
-    for (int r = 0; r < R; ++r) {
-        const float mA = credux_min(headA.x);
-        const float mB = credux_min(headB.x);
-        if (headA.x == mA) {
-            s.sel[r] = headA;
-            headA = nxtA;
-            colA += 32;
-            nxtA = colA[32];
-        }
-        if (headB.x == mB) {
-            sel2[r] = headB;
-            headB = nxtB;
-            colB += 32;
-            nxtB = colB[32];
-        }
-    }
     // both chains in one reduction: A's count in the low half, B's in the high half
-    const int popped = ((int)(colA - colA0) >> 5) + (((int)(colB - colB0) >> 5) << 16);
+    const int popped = pop_loop2<R>(s.lists, s.sel, lists2, sel2, lane);
     const int tot = __reduce_add_sync(FULL, popped);
     if ((tot & 0xffff) != R) pops_exact<Mem, R>(s, s.lists, s.sel, lane);
     if ((tot >> 16) != R) pops_exact<Mem, R>(s, lists2, sel2, lane);
