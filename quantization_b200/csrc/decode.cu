@@ -5,6 +5,8 @@
 // (N*K*D*4 bytes, 1-64 MB) are read through L2.  One warp owns one frame at a time; each lane owns 4 consecutive
 // features per 128-feature slab and adds the N selected rows in codebook order n = 0..N-1 in fp32, which is the
 // reference's sum(dim=0) order bit for bit (for N <= 16; torch re-associates longer sums, tests allow 1e-5 there).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mcq {
@@ -112,9 +114,150 @@ __global__ void __launch_bounds__(256) decode_kernel(const CT *__restrict__ code
     }
 }
 
+// ---- slab decode: large batches of byte codes ---------------------------------------------------------------------
+// decode_kernel above reads every selected row through L1 from L2: 16 KB of gathers per frame at 8 codebooks x 512
+// features for 2 KB written, and at ~1.1 Gvec/s it sits on the L2 -> SM rate (18 TB/s), not on HBM
+// (profiles/r01_search2.md).  Here a CTA owns a SLAB of 32 features: the 128-byte slab segments of all rows of the
+// first NS codebooks live in its shared memory (K * 128 bytes per codebook: 7 of 8 codebooks of 256 entries fit the
+// 227 KB; codebooks NS..N-1 are still read through L1), and the frames stream through it.  A quarter warp owns one
+// frame (8 lanes x float4 = the 128 bytes of the slab), so every shared-memory request is one conflict-free wavefront
+// per frame-row and every store a full 128-byte line.  Same arithmetic as decode_kernel: rows added in codebook order
+// n = 0..N-1 in fp32 -- bit-identical output.  L2 traffic per frame drops from N * D * 4 to (N - NS) * D * 4 bytes;
+// what remains is the shared-memory pipe itself (128 B/clk/SM: N loads + 1 store per 128 bytes written).
+constexpr int SLAB_W = 32;               // features per slab
+constexpr int SLAB_THREADS = 1024;       // 32 warps: 128 frames in flight per CTA
+constexpr int SLAB_SMEM_MAX = 227 * 1024 - 1024;
+
+// KT = 256: codebook_size known at compile time (row offsets become immediates and bytes cannot be out of range);
+// KT = 0: run-time codebook_size K <= 256.
+template <typename OT, int NT, int NS, int KT>
+__global__ void __launch_bounds__(SLAB_THREADS, 1)
+    decode_slab_kernel(const uint8_t *__restrict__ codes, int64_t B, int Krt, int D, int cps,
+                       const float *__restrict__ cs, OT *__restrict__ out) {
+    const int K = KT > 0 ? KT : Krt;
+    extern __shared__ __align__(16) float slab[];  // [NS * K][32]
+    const int nslabs = D / SLAB_W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fq = lane >> 3, sub = lane & 7;  // frame within the quad, float4 within the slab segment
+    const int64_t nquads = (B + 3) >> 2;
+    const unsigned kmask = (unsigned)(K - 1);
+    for (int u = blockIdx.x; u < nslabs * cps; u += gridDim.x) {
+        const int sl = u / cps, part = u - sl * cps;
+        const int d0 = sl * SLAB_W;
+        __syncthreads();  // the previous slab is no longer read
+        for (int i = threadIdx.x; i < NS * K * (SLAB_W / 4); i += SLAB_THREADS) {
+            const int row = i >> 3, c4 = i & 7;
+            reinterpret_cast<float4 *>(slab)[i] = __ldg(reinterpret_cast<const float4 *>(cs + (size_t)row * D + d0) + c4);
+        }
+        __syncthreads();
+        const float *gbase = cs + d0 + sub * 4;
+        const float *sbase = slab + sub * 4;
+        // quads of this part: q = part * 32 + warp, step cps * 32
+        int64_t q = (int64_t)part * 32 + warp;
+        const int64_t qstep = (int64_t)cps * 32;
+        unsigned c_lo = 0, c_hi = 0;
+        auto load_codes = [&](int64_t qq, unsigned &lo, unsigned &hi) {
+            int64_t b = qq * 4 + fq;
+            if (b >= B) b = B - 1;
+            if constexpr (NT == 8) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2 *>(codes + (size_t)b * 8));
+                lo = v.x;
+                hi = v.y;
+            } else {
+                lo = __ldg(reinterpret_cast<const unsigned *>(codes + (size_t)b * 4));
+                hi = 0;
+            }
+        };
+        if (q < nquads) load_codes(q, c_lo, c_hi);
+        for (; q < nquads; q += qstep) {
+            unsigned n_lo = 0, n_hi = 0;
+            if (q + qstep < nquads) load_codes(q + qstep, n_lo, n_hi);  // next quad's codes ahead of this quad's rows
+            float4 c[NT];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                unsigned k = __byte_perm(n < 4 ? c_lo : c_hi, 0, 0x4440 | (n & 3));  // byte n of the frame's codes
+                if (KT != 256 && k > kmask) k = 0;  // out-of-range codes decode as entry 0, like decode_kernel
+                if (n < NS)  // NS is a template parameter: resolved when the loop is unrolled
+                    c[n] = *reinterpret_cast<const float4 *>(sbase + k * SLAB_W + n * K * SLAB_W);
+                else
+                    c[n] = __ldg(reinterpret_cast<const float4 *>(gbase + (size_t)(n * K + (int)k) * D));
+            }
+            float4 acc = c[0];
+#pragma unroll
+            for (int n = 1; n < NT; ++n) {
+                acc.x = acc.x + c[n].x;
+                acc.y = acc.y + c[n].y;
+                acc.z = acc.z + c[n].z;
+                acc.w = acc.w + c[n].w;
+            }
+            const int64_t b = q * 4 + fq;
+            if (b < B) store4<OT>(out + (size_t)b * D + d0 + sub * 4, acc);
+            c_lo = n_lo;
+            c_hi = n_hi;
+        }
+    }
+}
+
+// frames from which the slab kernel is used (below it the fill of the slabs and the idle SMs of a small grid cost more
+// than the L2 gathers; MCQ_DECODE_SLAB=0 / 1 forces the choice for A/B measurements)
+constexpr int64_t SLAB_MIN_FRAMES = 16384;
+
+template <typename OT>
+int try_launch_decode_slab(const uint8_t *codes, int64_t B, int ncols, int N, int K, int D, const float *cs, OT *out,
+                           cudaStream_t st, bool *launched) {
+    *launched = false;
+    static int force = -1;
+    if (force < 0) {
+        const char *e = getenv("MCQ_DECODE_SLAB");
+        force = e ? (atoi(e) ? 1 : 0) : 2;
+    }
+    if (force == 0) return MCQ_OK;
+    if (ncols != N || (N != 4 && N != 8) || D % SLAB_W != 0 || reinterpret_cast<uintptr_t>(out) % 16 != 0 ||
+        reinterpret_cast<uintptr_t>(codes) % N != 0 || reinterpret_cast<uintptr_t>(cs) % 16 != 0)
+        return MCQ_OK;
+    if (force == 2 && B < SLAB_MIN_FRAMES) return MCQ_OK;
+    const int per_cb = K * SLAB_W * (int)sizeof(float);
+    int NS = SLAB_SMEM_MAX / per_cb;
+    if (NS > N) NS = N;
+    if (NS < N - 1 || NS < 1) return MCQ_OK;  // at most one codebook left to the L2 path
+    const int smem = NS * per_cb;
+    int dev = 0, sms = 148;
+    MCQ_CUDA(cudaGetDevice(&dev));
+    MCQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int nslabs = D / SLAB_W;
+    const int cps = sms / nslabs > 0 ? sms / nslabs : 1;  // CTAs per slab: 9 x 16 slabs = 144 CTAs at 512 features
+    int grid = nslabs * cps;
+    if (grid > sms) grid = sms;
+    auto launch = [&](auto kern) -> int {
+        MCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<grid, SLAB_THREADS, smem, st>>>(codes, B, K, D, cps, cs, out);
+        MCQ_LAUNCH_CHECK("decode_slab_kernel");
+        return MCQ_OK;
+    };
+    int rc;
+    if (N == 8 && K == 256)
+        rc = launch(decode_slab_kernel<OT, 8, 7, 256>);  // 7 x 32 KB of slab rows, the last codebook through L1
+    else if (N == 4 && K == 256)
+        rc = launch(decode_slab_kernel<OT, 4, 4, 256>);
+    else if (N == 8 && NS == 8)
+        rc = launch(decode_slab_kernel<OT, 8, 8, 0>);
+    else if (N == 4 && NS == 4)
+        rc = launch(decode_slab_kernel<OT, 4, 4, 0>);
+    else
+        return MCQ_OK;
+    if (rc == MCQ_OK) *launched = true;
+    return rc;
+}
+
 template <typename CT, typename OT>
 int launch_decode_t(const CT *codes, int64_t B, int ncols, int N, int K, int D, const float *cs, OT *out,
                     cudaStream_t st) {
+    if constexpr (sizeof(CT) == 1) {
+        bool launched = false;
+        const int rc = try_launch_decode_slab<OT>(reinterpret_cast<const uint8_t *>(codes), B, ncols, N, K, D, cs, out, st,
+                                                  &launched);
+        if (rc != MCQ_OK || launched) return rc;
+    }
     int64_t blocks = (B + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
     const unsigned g = (unsigned)blocks;

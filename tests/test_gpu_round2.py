@@ -322,3 +322,39 @@ def test_search_stats_count_executed_passes():
     q.encode(x, refine_indexes_iters=1)
     assert _lib.search_stats(ws, reset=True) == (B, B)
     assert _lib.search_stats(ws) == (0, 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Slab decode (decode.cu: decode_slab_kernel, used for >= 16,384 frames of byte codes): must equal the row-gather
+# kernel (which int64 indexes still take) bit for bit, and the CPU oracle on a prefix.
+@pytest.mark.parametrize("N,K,D,B", [(8, 256, 512, 70003), (8, 256, 768, 65536), (4, 256, 256, 131075),
+                                     (8, 64, 128, 65537), (8, 256, 1024, 66000), (4, 128, 96, 65540)])
+def test_decode_slab_matches_row_gather(N, K, D, B):
+    p = synth.synth_params(D, N, K, 3)
+    q = make_quantizer(D, N, K, p, DEV)
+    g = torch.Generator().manual_seed(99)
+    codes = torch.randint(0, K, (B, N), generator=g, dtype=torch.int64).to(torch.uint8)
+    if K < 256:
+        codes[5, 1] = 255  # out-of-range byte: both kernels decode it as entry 0
+    cd = codes.to(DEV)
+    c64 = cd.to(torch.int64)
+    idx64 = torch.where(c64 >= K, torch.zeros_like(c64), c64).contiguous()
+    with torch.no_grad():
+        slab = q.decode(cd)
+        rows = q.decode(idx64)
+        cs = q.get_centers().cpu().numpy()
+    assert torch.equal(slab, rows)
+    ref = oracle.decode(idx64[:1024].cpu().numpy(), cs)
+    assert np.array_equal(slab[:1024].cpu().numpy(), ref)
+    # half / bfloat16 outputs through the C ABI (Quantizer.decode returns fp32)
+    L = _lib.lib()
+    blob = q._prepared()
+    for dt, code in ((torch.float16, _lib.F16), (torch.bfloat16, _lib.BF16)):
+        a = torch.empty(B, D, dtype=dt, device=DEV)
+        b = torch.empty(B, D, dtype=dt, device=DEV)
+        _lib.check(L.mcq_decode(cd.data_ptr(), _lib.U8, B, N, N, K, D, blob.data_ptr(), a.data_ptr(), code,
+                                _lib.stream_ptr(DEV)), "mcq_decode")
+        _lib.check(L.mcq_decode(idx64.data_ptr(), _lib.I64, B, N, N, K, D, blob.data_ptr(), b.data_ptr(), code,
+                                _lib.stream_ptr(DEV)), "mcq_decode")
+        torch.cuda.synchronize()
+        assert torch.equal(a, b)
