@@ -613,7 +613,23 @@ def run_ours(args, rank, world, local_rank):
     e2e_ms = float(t.item())
     e2e_value = world * B / (e2e_ms * 1e-3) / 1e6
     same_codes = bool(torch.equal(out_host, codes.cpu()))
-    del xp
+    # the host -> device copy of a step's frames ALONE, all ranks at once: what the host side of the box can feed.
+    # (e2e can be no faster than this; at 8 ranks the eight 2 GiB streams share one host memory system.)
+    xd = torch.empty_like(x)
+    xd.copy_(xp, non_blocking=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        xd.copy_(xp, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    h2d_alone_ms = float(t.item())
+    del xp, xd
 
     # ---- decode (HBM-bound leg of the path), reported beside the encode number
     with torch.no_grad():
@@ -703,7 +719,11 @@ def run_ours(args, rank, world, local_rank):
                    "exchange": "NCCL all-gather of the uint8 codes" if world > 1 else "none (1 GPU)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * DIM * 4, "d2h_bytes_per_step": B * NCB,
                 "ms_per_step": e2e_ms, "api": "Quantizer.encode_host -> mcq_encode_host (pinned host buffers)",
-                "codes_equal_device_path": same_codes},
+                "codes_equal_device_path": same_codes,
+                "h2d_alone_ms": h2d_alone_ms,
+                "h2d_alone_GBps_per_rank": B * DIM * 4 / (h2d_alone_ms * 1e-3) / 1e9,
+                "h2d_note": "h2d_alone_ms = the step's 2 GiB host->device copy with nothing else running, all ranks "
+                            "at once (max over ranks): the floor the host memory system / PCIe sets for e2e"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
