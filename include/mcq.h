@@ -15,7 +15,8 @@
  *   mcq_decode_backward  <- autograd of decode w.r.t. the scaled centers (used by compute_loss, :213-216)
  *   mcq_class_loss_*     <- the log-softmax / chosen-logprob / mean-probability part of compute_loss (:218-240)
  *   mcq_encode_host      <- the same encode for a caller that holds HOST buffers (what a cgo/JNI/ctypes
- *                           host without its own CUDA plumbing binds)
+ *                           host without its own CUDA plumbing binds);
+ *                           mcq_encode_host_ws is its re-entrant form (caller-owned staging buffer and stream)
  *
  * Conventions: plain pointers and sizes only.  Every function returns 0 on success or a negative
  * MCQ_E* code; mcq_last_error() gives the thread's last message.  Unless the name ends in _host,
@@ -227,6 +228,21 @@ int mcq_search_stats(void *workspace, int reset, uint64_t *passes_frames, void *
 int mcq_encode_host(const void *x_host, int x_dtype, int64_t num_frames, int dim, int num_codebooks,
                     int codebook_size, const void *prepared, int iters, void *codes_host, int codes_dtype,
                     int device);
+
+/*
+ * The re-entrant form of the host-buffer encode (what a multi-threaded host binds): the CALLER owns the device staging
+ * buffer (`staging`, at least mcq_encode_host_ws_bytes(...) bytes on the current device; a smaller buffer only shrinks
+ * the chunks) and the stream.  Nothing is allocated, no state survives the call, the host is not blocked: the copies
+ * and kernels are ordered after everything already on `stream`, and `stream` completes when codes_host is complete
+ * (synchronise it, or record an event on it, before reading codes_host or reusing x_host / staging).  x_host and
+ * codes_host should be pinned (cudaHostAlloc / cudaHostRegister) for the copies to overlap the kernels.
+ * Replaces the same call sites as mcq_encode_host: Quantizer.encode (quantization.py:244-275) on host tensors.
+ */
+size_t mcq_encode_host_ws_bytes(int64_t num_frames, int dim, int num_codebooks, int codebook_size, int x_dtype,
+                                int codes_dtype);
+int mcq_encode_host_ws(const void *x_host, int x_dtype, int64_t num_frames, int dim, int num_codebooks,
+                       int codebook_size, const void *prepared, int iters, void *codes_host, int codes_dtype,
+                       void *staging, size_t staging_bytes, void *stream);
 
 #ifdef __cplusplus
 }

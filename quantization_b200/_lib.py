@@ -55,6 +55,8 @@ def lib():
         "mcq_xct": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, vp, sz, vp]),
         "mcq_search": (i32, [vp, vp, i64, i32, i32, i32, vp, vp, vp]),
         "mcq_encode_host": (i32, [vp, i32, i64, i32, i32, i32, vp, i32, vp, i32, i32]),
+        "mcq_encode_host_ws_bytes": (sz, [i64, i32, i32, i32, i32, i32]),
+        "mcq_encode_host_ws": (i32, [vp, i32, i64, i32, i32, i32, vp, i32, vp, i32, vp, sz, vp]),
         "mcq_recon_loss_partials": (i32, []),
         "mcq_recon_loss_forward": (i32, [vp, i32, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp]),
         "mcq_recon_loss_backward": (i32, [vp, i32, vp, i64, i32, i32, i32, vp, vp, vp, vp]),
@@ -82,6 +84,7 @@ EXPORTS = ["mcq_version", "mcq_last_error", "mcq_packed_cols", "mcq_prepared_byt
            "mcq_prepare", "mcq_encode", "mcq_refine", "mcq_decode", "mcq_decode_centers", "mcq_decode_backward",
            "mcq_class_loss_forward", "mcq_class_loss_backward", "mcq_class_loss_partials",
            "mcq_prepared_scaled_centers", "mcq_prepared_gram", "mcq_xct", "mcq_search", "mcq_encode_host",
+           "mcq_encode_host_ws_bytes", "mcq_encode_host_ws",
            "mcq_recon_loss_partials", "mcq_recon_loss_forward", "mcq_recon_loss_backward",
            "mcq_gemm_tn_workspace_bytes", "mcq_gemm_tn", "mcq_gemm_nt_workspace_bytes", "mcq_gemm_nt",
            "mcq_jcl_hidden_forward", "mcq_jcl_hidden_backward", "mcq_jcl_partials", "mcq_jcl_cross_entropy",

@@ -85,6 +85,36 @@ int encode_host_locked(HostCtx &c, const void *x_host, int x_dtype, int64_t B, i
     return MCQ_OK;
 }
 
+// Layout of the caller-owned staging buffer of mcq_encode_host_ws for chunks of Bc frames: two frame buffers, two
+// code buffers, one mcq_encode workspace (every region 1024-byte aligned).
+struct HostWs {
+    int64_t Bc;
+    size_t off_x[2], off_codes[2], off_ws, ws_bytes, bytes;
+};
+
+HostWs host_ws_layout(int64_t Bc, int D, int N, int K, int x_dtype, int codes_dtype) {
+    HostWs L;
+    L.Bc = Bc;
+    const size_t xelt = x_dtype == MCQ_F32 ? 4 : 2;
+    const int ncols = codes_dtype == MCQ_U8 ? mcq_packed_cols(N, K) : N;
+    const size_t celt = codes_dtype == MCQ_U8 ? 1 : (codes_dtype == MCQ_I64 ? 8 : 4);
+    size_t off = 0;
+    for (int k = 0; k < 2; ++k) {
+        L.off_x[k] = off;
+        off += align_up((size_t)Bc * D * xelt, 1024);
+    }
+    for (int k = 0; k < 2; ++k) {
+        L.off_codes[k] = off;
+        off += align_up((size_t)Bc * ncols * celt, 1024);
+    }
+    L.off_ws = off;
+    L.ws_bytes = mcq_workspace_bytes(Bc, D, N, K);
+    L.bytes = off + align_up(L.ws_bytes, 1024);
+    return L;
+}
+
+constexpr int64_t HOST_CHUNK = 148 * 128 * 2;  // 37,888 frames: two waves of 128-row GEMM tiles
+
 }  // namespace
 
 }  // namespace mcq
@@ -130,4 +160,98 @@ extern "C" int mcq_encode_host(const void *x_host, int x_dtype, int64_t B, int D
         if (e != cudaSuccess) rc = cuda_fail(e, "mcq_encode_host: stream synchronisation");
     }
     return rc;
+}
+
+extern "C" size_t mcq_encode_host_ws_bytes(int64_t num_frames, int D, int N, int K, int x_dtype, int codes_dtype) {
+    if (check_shape(N, K, D) || num_frames < 1 || x_dtype < 0 || x_dtype > 2 || codes_dtype < 0 || codes_dtype > 2)
+        return 0;
+    int64_t Bc = HOST_CHUNK;
+    if (Bc > num_frames) Bc = (int64_t)align_up((size_t)num_frames, 128);
+    return host_ws_layout(Bc, D, N, K, x_dtype, codes_dtype).bytes;
+}
+
+// The re-entrant form: the caller owns the device staging buffer and the stream; nothing is allocated, no state is
+// kept between calls and the host is never blocked.  The copies and kernels run on two helper streams created and
+// released inside the call (stream / event destruction is deferred by the driver until their work has drained), ordered
+// after everything already on `stream`, and `stream` is made to wait for the last of them.
+extern "C" int mcq_encode_host_ws(const void *x_host, int x_dtype, int64_t B, int D, int N, int K, const void *prepared,
+                                  int iters, void *codes_host, int codes_dtype, void *staging, size_t staging_bytes,
+                                  void *stream) {
+    int rc = check_shape(N, K, D);
+    if (rc) return rc;
+    if (B < 0 || iters < 0 || x_dtype < 0 || x_dtype > 2 || codes_dtype < 0 || codes_dtype > 2) {
+        set_error("mcq_encode_host_ws: bad argument");
+        return MCQ_EINVAL;
+    }
+    if (B == 0) return MCQ_OK;
+    if (!x_host || !prepared || !codes_host || !staging) {
+        set_error("mcq_encode_host_ws: null pointer");
+        return MCQ_EINVAL;
+    }
+    // the largest chunk (a multiple of 128 frames, at most HOST_CHUNK) whose layout fits the caller's buffer
+    int64_t Bc = HOST_CHUNK;
+    if (Bc > B) Bc = (int64_t)align_up((size_t)B, 128);
+    while (Bc >= 128 && host_ws_layout(Bc, D, N, K, x_dtype, codes_dtype).bytes > staging_bytes) Bc -= 128;
+    if (Bc < 128) {
+        set_error("mcq_encode_host_ws: staging buffer of %zu bytes is too small (mcq_encode_host_ws_bytes)", staging_bytes);
+        return MCQ_EINVAL;
+    }
+    const HostWs L = host_ws_layout(Bc, D, N, K, x_dtype, codes_dtype);
+    const size_t xelt = x_dtype == MCQ_F32 ? 4 : 2;
+    const int ncols = codes_dtype == MCQ_U8 ? mcq_packed_cols(N, K) : N;
+    const size_t celt = codes_dtype == MCQ_U8 ? 1 : (codes_dtype == MCQ_I64 ? 8 : 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    char *base = (char *)staging;
+
+    struct Res {  // released on every exit path; destruction of busy streams / events is deferred by the driver
+        cudaStream_t s_in = nullptr, s_out = nullptr;
+        cudaEvent_t ev_start = nullptr, ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr},
+                    ev_out[2] = {nullptr, nullptr};
+        ~Res() {
+            for (int k = 0; k < 2; ++k) {
+                if (ev_in[k]) cudaEventDestroy(ev_in[k]);
+                if (ev_cmp[k]) cudaEventDestroy(ev_cmp[k]);
+                if (ev_out[k]) cudaEventDestroy(ev_out[k]);
+            }
+            if (ev_start) cudaEventDestroy(ev_start);
+            if (s_in) cudaStreamDestroy(s_in);
+            if (s_out) cudaStreamDestroy(s_out);
+        }
+    } r;
+    MCQ_CUDA(cudaStreamCreateWithFlags(&r.s_in, cudaStreamNonBlocking));
+    MCQ_CUDA(cudaStreamCreateWithFlags(&r.s_out, cudaStreamNonBlocking));
+    MCQ_CUDA(cudaEventCreateWithFlags(&r.ev_start, cudaEventDisableTiming));
+    for (int k = 0; k < 2; ++k) {
+        MCQ_CUDA(cudaEventCreateWithFlags(&r.ev_in[k], cudaEventDisableTiming));
+        MCQ_CUDA(cudaEventCreateWithFlags(&r.ev_cmp[k], cudaEventDisableTiming));
+        MCQ_CUDA(cudaEventCreateWithFlags(&r.ev_out[k], cudaEventDisableTiming));
+    }
+    // everything already enqueued on the caller's stream (e.g. mcq_prepare, earlier users of `staging`) comes first
+    MCQ_CUDA(cudaEventRecord(r.ev_start, st));
+    MCQ_CUDA(cudaStreamWaitEvent(r.s_in, r.ev_start, 0));
+    MCQ_CUDA(cudaStreamWaitEvent(r.s_out, r.ev_start, 0));
+    int64_t chunk = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += Bc, ++chunk) {
+        const int k = (int)(chunk & 1);
+        const int64_t nb = B - b0 < Bc ? B - b0 : Bc;
+        if (chunk >= 2) MCQ_CUDA(cudaStreamWaitEvent(r.s_in, r.ev_cmp[k], 0));  // x buffer k was read by chunk - 2
+        MCQ_CUDA(cudaMemcpyAsync(base + L.off_x[k], (const char *)x_host + (size_t)b0 * D * xelt, (size_t)nb * D * xelt,
+                                 cudaMemcpyHostToDevice, r.s_in));
+        MCQ_CUDA(cudaEventRecord(r.ev_in[k], r.s_in));
+        MCQ_CUDA(cudaStreamWaitEvent(st, r.ev_in[k], 0));
+        if (chunk >= 2) MCQ_CUDA(cudaStreamWaitEvent(st, r.ev_out[k], 0));  // code buffer k was copied out by chunk - 2
+        if ((rc = mcq_encode(base + L.off_x[k], x_dtype, nb, D, N, K, prepared, iters, base + L.off_codes[k], codes_dtype,
+                             base + L.off_ws, L.ws_bytes, st)))
+            return rc;
+        MCQ_CUDA(cudaEventRecord(r.ev_cmp[k], st));
+        MCQ_CUDA(cudaStreamWaitEvent(r.s_out, r.ev_cmp[k], 0));
+        MCQ_CUDA(cudaMemcpyAsync((char *)codes_host + (size_t)b0 * ncols * celt, base + L.off_codes[k],
+                                 (size_t)nb * ncols * celt, cudaMemcpyDeviceToHost, r.s_out));
+        MCQ_CUDA(cudaEventRecord(r.ev_out[k], r.s_out));
+    }
+    // the caller's stream completes when the last codes are in host memory (both helper streams are joined)
+    for (int k = 0; k < 2; ++k) {
+        if (chunk > k) MCQ_CUDA(cudaStreamWaitEvent(st, r.ev_out[k], 0));
+    }
+    return MCQ_OK;
 }

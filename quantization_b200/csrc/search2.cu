@@ -607,14 +607,21 @@ __device__ __forceinline__ void merge4_final(WarpMem2<N> &s, const float *__rest
     float dot[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) dot[i] = 0.0f;
-    // table T_ab: lane (hi, q) computes rows p = 8*hi + t of column q -- a request reads two G rows x 16 columns
+    // table T_ab: lane (hi, q) computes rows p = 8*hi + t of column q -- a request reads two G rows x 16 columns.
+    // Only the slots the 32 + 32 candidates still use matter (5.8 of 16 per codebook on average, tools note in
+    // profiles/r02_search.md): the columns of a table are COMPACTED to the used slots of codebook b (column q goes to
+    // position popc(used_b below q)), so that a candidate row folds ceil(nq / 4) float4 instead of 4, and rows no
+    // candidate uses are neither gathered nor stored.  Same values, same order of additions per (i, j).
     const int q = lane & 15, pb = (lane >> 4) * 8;
-    const int tbase = trow_off(pb) + q;
+    const unsigned below_q = (1u << q) - 1u;
 #pragma unroll 1
     for (int lb = 0; lb < 4; ++lb) {
         const int b = 4 + lb;
+        const unsigned ub = s.used[4 + lb];
+        const int nq4 = (__popc(ub) + 3) >> 2;                 // float4 groups of a compacted table row (warp-uniform)
+        const int tbase = trow_off(pb) + __popc(ub & below_q);  // my compacted column
         const unsigned cq = b * K2 + s.kk[b][q];
-        const bool colu = (s.used[4 + lb] >> q) & 1u;  // does any candidate still use slot q of codebook b?
+        const bool colu = (ub >> q) & 1u;  // does any candidate still use slot q of codebook b?
         const unsigned cbo = b * K2 + s.old[b];
         float E[16];
 #pragma unroll
@@ -625,17 +632,18 @@ __device__ __forceinline__ void merge4_final(WarpMem2<N> &s, const float *__rest
 #pragma unroll 1
         for (int ap = 0; ap < 4; ap += 2) {
             float gv[2][8], w[2];
+            unsigned msk[2];
 #pragma unroll
             for (int aa = 0; aa < 2; ++aa) {
                 const int a = ap + aa;
-                const unsigned msk = colu ? (s.used[a] >> pb) & 0xffu : 0u;  // rows of my half that are still in use
+                msk[aa] = colu ? (s.used[a] >> pb) & 0xffu : 0u;  // rows of my half that are still in use
                 const uint4 *rp = reinterpret_cast<const uint4 *>(&s.rowk[a][pb]);
                 const uint4 r0 = rp[0], r1 = rp[1];
                 const unsigned ra[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     gv[aa][t] = 0.0f;
-                    if ((msk >> t) & 1u) gv[aa][t] = gat(G, ra[t] + cq);
+                    if ((msk[aa] >> t) & 1u) gv[aa][t] = gat(G, ra[t] + cq);
                 }
                 w[aa] = gat(G, s.rowoff[a] + cbo);
             }
@@ -648,7 +656,8 @@ __device__ __forceinline__ void merge4_final(WarpMem2<N> &s, const float *__rest
                 const float v = s.uv[b][a][q];
 #pragma unroll
                 for (int t = 0; t < 8; ++t)
-                    tabs[aa][tbase + t * TSTR] = ((gv[aa][t] - u[t]) - v) + w[aa];  // tbase + t*TSTR = trow_off(pb+t) + q
+                    if ((msk[aa] >> t) & 1u)  // tbase + t*TSTR = trow_off(pb + t) + compacted column
+                        tabs[aa][tbase + t * TSTR] = ((gv[aa][t] - u[t]) - v) + w[aa];
             }
             __syncwarp();
 #pragma unroll
@@ -657,18 +666,21 @@ __device__ __forceinline__ void merge4_final(WarpMem2<N> &s, const float *__rest
                     reinterpret_cast<const float4 *>(&tabs[aa][trow_off((ti >> (4 * (ap + aa))) & 15)]);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const float4 r = mine[c];
-                    fadd2(E[4 * c + 0], E[4 * c + 1], r.x, r.y);
-                    fadd2(E[4 * c + 2], E[4 * c + 3], r.z, r.w);
+                    if (c < nq4) {
+                        const float4 r = mine[c];
+                        fadd2(E[4 * c + 0], E[4 * c + 1], r.x, r.y);
+                        fadd2(E[4 * c + 2], E[4 * c + 3], r.z, r.w);
+                    }
                 }
             }
             __syncwarp();
         }
         float4 *erow = reinterpret_cast<float4 *>(&s.es[lane][0]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) erow[c] = make_float4(E[4 * c], E[4 * c + 1], E[4 * c + 2], E[4 * c + 3]);
+        for (int c = 0; c < 4; ++c)
+            if (c < nq4) erow[c] = make_float4(E[4 * c], E[4 * c + 1], E[4 * c + 2], E[4 * c + 3]);
         __syncwarp();
-        const int jq = (tj >> (4 * lb)) & 15;
+        const int jq = __popc(ub & ((1u << ((tj >> (4 * lb)) & 15)) - 1u));  // compacted column of my slot of codebook b
 #pragma unroll
         for (int i = 0; i < 32; ++i) dot[i] = dot[i] + s.es[i][jq];
         __syncwarp();

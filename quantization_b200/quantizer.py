@@ -288,9 +288,12 @@ class Quantizer(nn.Module):
         return codes.reshape(*x.shape[:-1], codes.shape[-1])
 
     def encode_host(self, x: Tensor, refine_indexes_iters: int = 5, as_bytes: bool = True,
-                    out: Optional[Tensor] = None) -> Tensor:
+                    out: Optional[Tensor] = None, library_buffers: bool = False) -> Tensor:
         """Extension: `x` (*, dim) lives in HOST memory (ideally pinned); returns host codes.  Chunks are streamed
-        through the device with copies overlapping the kernels (mcq_encode_host)."""
+        through the device with the copies overlapping the kernels.  Default: mcq_encode_host_ws -- the staging
+        buffer is a PyTorch tensor cached on the quantizer, the work is ordered on the current stream, which is
+        synchronised before returning.  library_buffers=True: mcq_encode_host (the library's own cached device
+        buffers; what a host without CUDA plumbing of its own binds)."""
         if x.is_cuda:
             raise RuntimeError("encode_host expects a host tensor; use encode() for device tensors")
         x2 = x.reshape(-1, self.dim).contiguous()
@@ -301,14 +304,30 @@ class Quantizer(nn.Module):
         dev = self.centers.device
         cols = L.mcq_packed_cols(N, K) if as_bytes else N
         dt = torch.uint8 if as_bytes else torch.int64
+        cdt = _lib.U8 if as_bytes else _lib.I64
         if out is None:
             out = torch.empty(B, cols, dtype=dt, pin_memory=True)
         assert out.shape == (B, cols) and out.dtype == dt and out.is_contiguous() and not out.is_cuda
-        torch.cuda.current_stream(dev).synchronize()  # the blob may just have been rebuilt on this stream
-        rc = L.mcq_encode_host(x2.data_ptr(), _lib.x_dtype_code(x2), B, D, N, K, blob.data_ptr(),
-                               int(refine_indexes_iters), out.data_ptr(), _lib.U8 if as_bytes else _lib.I64,
-                               dev.index if dev.index is not None else torch.cuda.current_device())
-        _lib.check(rc, "mcq_encode_host")
+        if B == 0:
+            return out.reshape(*x.shape[:-1], cols)
+        if library_buffers:
+            torch.cuda.current_stream(dev).synchronize()  # the blob may just have been rebuilt on this stream
+            rc = L.mcq_encode_host(x2.data_ptr(), _lib.x_dtype_code(x2), B, D, N, K, blob.data_ptr(),
+                                   int(refine_indexes_iters), out.data_ptr(), cdt,
+                                   dev.index if dev.index is not None else torch.cuda.current_device())
+            _lib.check(rc, "mcq_encode_host")
+            return out.reshape(*x.shape[:-1], cols)
+        need = int(L.mcq_encode_host_ws_bytes(B, D, N, K, _lib.x_dtype_code(x2), cdt))
+        st = getattr(self, "_host_staging", None)
+        if st is None or st.device != dev or st.numel() < need:
+            st = torch.empty(need, dtype=torch.uint8, device=dev)
+            self._host_staging = st
+        with torch.cuda.device(dev):
+            rc = L.mcq_encode_host_ws(x2.data_ptr(), _lib.x_dtype_code(x2), B, D, N, K, blob.data_ptr(),
+                                      int(refine_indexes_iters), out.data_ptr(), cdt, st.data_ptr(), st.numel(),
+                                      _lib.stream_ptr(dev))
+        _lib.check(rc, "mcq_encode_host_ws")
+        torch.cuda.current_stream(dev).synchronize()  # the codes are in host memory when the stream has drained
         return out.reshape(*x.shape[:-1], cols)
 
     def _compute_indexes(self, x: Tensor, refine_indexes_iters: int = 3) -> Tensor:

@@ -549,6 +549,39 @@ def test_encode_host_matches_device():
     out = q.encode_host(xp)
     assert not out.is_cuda and torch.equal(out, q.encode(x.to(DEV)).cpu())
     assert torch.equal(q.encode_host(x), out)  # pageable host memory works too
+    assert torch.equal(q.encode_host(xp, library_buffers=True), out)  # mcq_encode_host: the library's own buffers
+    assert torch.equal(q.encode_host(xp, as_bytes=False), q.encode(x.to(DEV), as_bytes=False).cpu())
+
+
+def test_encode_host_ws_is_stream_ordered_and_reentrant():
+    """mcq_encode_host_ws: caller-owned staging buffer, caller's stream, no host synchronisation.  Two calls on two
+    streams with two staging buffers run concurrently; a staging buffer smaller than mcq_encode_host_ws_bytes only
+    shrinks the chunks; one too small for a 128-frame chunk is refused."""
+    D, N, K, B = 128, 4, 256, 60000
+    p = synth.synth_params(D, N, K, 5)
+    q = make_quantizer(D, N, K, p, DEV)
+    L = _lib.lib()
+    blob = q._prepared()
+    torch.cuda.synchronize()
+    xs = [synth.synth_x(B, D, 21 + i).pin_memory() for i in range(2)]
+    want = [q.encode(x.to(DEV)).cpu() for x in xs]
+    need = int(L.mcq_encode_host_ws_bytes(B, D, N, K, _lib.F32, _lib.U8))
+    assert need > 0
+    stagings = [torch.empty(need, dtype=torch.uint8, device=DEV), torch.empty(need // 3, dtype=torch.uint8, device=DEV)]
+    outs = [torch.zeros(B, N, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    streams = [torch.cuda.Stream(DEV), torch.cuda.Stream(DEV)]
+    for x, st, out, stream in zip(xs, stagings, outs, streams):
+        rc = L.mcq_encode_host_ws(x.data_ptr(), _lib.F32, B, D, N, K, blob.data_ptr(), 5, out.data_ptr(), _lib.U8,
+                                  st.data_ptr(), st.numel(), stream.cuda_stream)
+        _lib.check(rc, "mcq_encode_host_ws")
+    for stream in streams:
+        stream.synchronize()
+    for out, w in zip(outs, want):
+        assert torch.equal(out, w)
+    tiny = torch.empty(4096, dtype=torch.uint8, device=DEV)
+    rc = L.mcq_encode_host_ws(xs[0].data_ptr(), _lib.F32, B, D, N, K, blob.data_ptr(), 5, outs[0].data_ptr(), _lib.U8,
+                              tiny.data_ptr(), tiny.numel(), streams[0].cuda_stream)
+    assert rc != 0 and b"too small" in L.mcq_last_error()
 
 
 @pytest.mark.parametrize("K,N,B", [(16, 4, 512), (256, 4, 1000), (64, 2, 777), (32, 8, 130), (256, 32, 96), (16, 64, 100),
