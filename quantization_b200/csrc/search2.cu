@@ -896,14 +896,18 @@ __device__ __forceinline__ void wide_dots(WarpMem16 &s, const float *__restrict_
 #pragma unroll
     for (int i = 0; i < 32; ++i) dot[i] = 0.0f;
     if constexpr (NA == 4) gather_uv_local<4, 4>(s, G, a_base, b_base, lane);  // all 16 pairs fit: c = la * 4 + lb
+    // as in merge4_final: table columns compacted to the slots of codebook b that are still in use, unused rows skipped
     const int q = lane & 15, pb = (lane >> 4) * 8;
-    const int tbase = trow_off(pb) + q;
+    const unsigned below_q = (1u << q) - 1u;
 #pragma unroll 1
     for (int lb = 0; lb < NA; ++lb) {
         const int b = b_base + lb;
         if constexpr (NA == 8) gather_uv_local<8, 1>(s, G, a_base, b, lane);   // the 8 pairs of this b: c = la
+        const unsigned ub = s.used[8 + lb];
+        const int nq4 = (__popc(ub) + 3) >> 2;
+        const int tbase = trow_off(pb) + __popc(ub & below_q);
         const unsigned cq = b * K2 + s.kk[b][q];
-        const bool colu = (s.used[8 + lb] >> q) & 1u;
+        const bool colu = (ub >> q) & 1u;
         const unsigned cbo = b * K2 + s.old[b];
         float E[16];
 #pragma unroll
@@ -932,22 +936,26 @@ __device__ __forceinline__ void wide_dots(WarpMem16 &s, const float *__restrict_
             const float v = s.vl[c][q];
             const float w = gat(G, s.rowoff[a] + cbo);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) s.tab[tbase + t * TSTR] = ((gv[t] - u[t]) - v) + w;  // = trow_off(pb + t) + q
+            for (int t = 0; t < 8; ++t)
+                if ((msk >> t) & 1u) s.tab[tbase + t * TSTR] = ((gv[t] - u[t]) - v) + w;  // trow_off(pb + t) + compacted column
             __syncwarp();
             const float4 *mine = reinterpret_cast<const float4 *>(&s.tab[trow_off((ti >> (4 * la)) & 15)]);
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
-                const float4 r = mine[cc];
-                fadd2(E[4 * cc + 0], E[4 * cc + 1], r.x, r.y);
-                fadd2(E[4 * cc + 2], E[4 * cc + 3], r.z, r.w);
+                if (cc < nq4) {
+                    const float4 r = mine[cc];
+                    fadd2(E[4 * cc + 0], E[4 * cc + 1], r.x, r.y);
+                    fadd2(E[4 * cc + 2], E[4 * cc + 3], r.z, r.w);
+                }
             }
             __syncwarp();
         }
         float4 *erow = reinterpret_cast<float4 *>(&s.es[lane][0]);
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) erow[cc] = make_float4(E[4 * cc], E[4 * cc + 1], E[4 * cc + 2], E[4 * cc + 3]);
+        for (int cc = 0; cc < 4; ++cc)
+            if (cc < nq4) erow[cc] = make_float4(E[4 * cc], E[4 * cc + 1], E[4 * cc + 2], E[4 * cc + 3]);
         __syncwarp();
-        const int jq = (tj >> (4 * lb)) & 15;
+        const int jq = __popc(ub & ((1u << ((tj >> (4 * lb)) & 15)) - 1u));
 #pragma unroll
         for (int i = 0; i < 32; ++i) dot[i] = dot[i] + s.es[i][jq];
         __syncwarp();
