@@ -718,7 +718,7 @@ def run_ours(args, rank, world, local_rank):
                    "frames_per_gpu": B, "l2": "inputs (2 GiB of frames per step) exceed the 126 MB L2; no flush needed",
                    "exchange": "NCCL all-gather of the uint8 codes" if world > 1 else "none (1 GPU)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * DIM * 4, "d2h_bytes_per_step": B * NCB,
-                "ms_per_step": e2e_ms, "api": "Quantizer.encode_host -> mcq_encode_host (pinned host buffers)",
+                "ms_per_step": e2e_ms, "api": "Quantizer.encode_host -> mcq_encode_host_ws (pinned host buffers, PyTorch-owned device staging, current stream)",
                 "codes_equal_device_path": same_codes,
                 "h2d_alone_ms": h2d_alone_ms,
                 "h2d_alone_GBps_per_rank": B * DIM * 4 / (h2d_alone_ms * 1e-3) / 1e9,
