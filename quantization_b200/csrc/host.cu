@@ -113,7 +113,9 @@ HostWs host_ws_layout(int64_t Bc, int D, int N, int K, int x_dtype, int codes_dt
     return L;
 }
 
-constexpr int64_t HOST_CHUNK = 148 * 128 * 2;  // 37,888 frames: two waves of 128-row GEMM tiles
+constexpr int64_t HOST_CHUNK = 148 * 128 * 4;  // 75,776 frames: one chunk of mcq_encode (four waves of GEMM tiles)
+constexpr int64_t HOST_FIRST = 148 * 128;      // ramp: chunks of 1, 2, then 4 waves -- the first copy is the only one
+                                               // nothing hides, and each later copy must fit under the compute before it
 
 }  // namespace
 
@@ -231,9 +233,10 @@ extern "C" int mcq_encode_host_ws(const void *x_host, int x_dtype, int64_t B, in
     MCQ_CUDA(cudaStreamWaitEvent(r.s_in, r.ev_start, 0));
     MCQ_CUDA(cudaStreamWaitEvent(r.s_out, r.ev_start, 0));
     int64_t chunk = 0;
-    for (int64_t b0 = 0; b0 < B; b0 += Bc, ++chunk) {
+    for (int64_t b0 = 0, nb = 0; b0 < B; b0 += nb, ++chunk) {
         const int k = (int)(chunk & 1);
-        const int64_t nb = B - b0 < Bc ? B - b0 : Bc;
+        nb = B - b0 < Bc ? B - b0 : Bc;
+        if (chunk < 2 && nb > (HOST_FIRST << chunk)) nb = HOST_FIRST << chunk;
         if (chunk >= 2) MCQ_CUDA(cudaStreamWaitEvent(r.s_in, r.ev_cmp[k], 0));  // x buffer k was read by chunk - 2
         MCQ_CUDA(cudaMemcpyAsync(base + L.off_x[k], (const char *)x_host + (size_t)b0 * D * xelt, (size_t)nb * D * xelt,
                                  cudaMemcpyHostToDevice, r.s_in));
