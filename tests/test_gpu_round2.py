@@ -328,7 +328,8 @@ def test_search_stats_count_executed_passes():
 # Slab decode (decode.cu: decode_slab_kernel, used for >= 16,384 frames of byte codes): must equal the row-gather
 # kernel (which int64 indexes still take) bit for bit, and the CPU oracle on a prefix.
 @pytest.mark.parametrize("N,K,D,B", [(8, 256, 512, 70003), (8, 256, 768, 65536), (4, 256, 256, 131075),
-                                     (8, 64, 128, 65537), (8, 256, 1024, 66000), (4, 128, 96, 65540)])
+                                     (8, 64, 128, 65537), (8, 256, 1024, 66000), (4, 128, 96, 65540),
+                                     (4, 64, 4800, 16400)])  # the last: 150 slabs > 148 CTAs, a CTA walks two slabs
 def test_decode_slab_matches_row_gather(N, K, D, B):
     p = synth.synth_params(D, N, K, 3)
     q = make_quantizer(D, N, K, p, DEV)
@@ -358,3 +359,25 @@ def test_decode_slab_matches_row_gather(N, K, D, B):
                                 _lib.stream_ptr(DEV)), "mcq_decode")
         torch.cuda.synchronize()
         assert torch.equal(a, b)
+
+
+def test_decode_slab_under_cuda_graph_capture():
+    """The slab decode launch (function attribute + launch, no allocation, no synchronisation) can be captured."""
+    N, K, D, B = 8, 256, 512, 20000
+    q = make_quantizer(D, N, K, synth.synth_params(D, N, K, 4), DEV)
+    codes = torch.randint(0, K, (B, N), dtype=torch.uint8, device=DEV)
+    L = _lib.lib()
+    blob = q._prepared()
+    out = torch.zeros(B, D, dtype=torch.float32, device=DEV)
+    with torch.no_grad():
+        want = q.decode(codes)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream(DEV)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            _lib.check(L.mcq_decode(codes.data_ptr(), _lib.U8, B, N, N, K, D, blob.data_ptr(), out.data_ptr(), _lib.F32,
+                                    _lib.stream_ptr(DEV)), "mcq_decode")
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
