@@ -102,19 +102,27 @@ struct alignas(16) WarpMem2 {
         float tab[TAB_FLOATS];   // T_ab of the quad merge (trow_off)
         float2 lists2[10][32];   // second column set of the interleaved merge selections (merge1_pair, merge2_pair)
     };
+    float2 sel[32];          // result of the current selection: (key, flat), ascending
+    float2 sel2[32];         // result of the second of two interleaved merge selections
+    float kd2[NG2][16];      // kept deltas / slot tuples after the first merge
+    unsigned kt2[NG2][16];
 #else
-    float tab[TAB_FLOATS];   // T_ab of the quad merge (trow_off)
+    // the quad merge's table never lives at the same time as the selection results and the first merge's survivors
+    // (they are dead once the second merge has stored kd3 / kt3): sharing the bytes keeps 16 warps under 164 KB, the
+    // next smaller shared-memory carve-out, which leaves L1 92 KB instead of 60
+    union {
+        float tab[TAB_FLOATS];   // T_ab of the quad merge (trow_off)
+        struct {
+            float2 sel[32];      // result of the current selection: (key, flat), ascending
+            float kd2[NG2][16];  // kept deltas / slot tuples after the first merge
+            unsigned kt2[NG2][16];
+        };
+    };
 #endif
     float kd1[N][16];        // level-1 kept candidates of each codebook: delta ...
     int kk[N][16];           // ... and codebook entry k
     unsigned rowk[N][16];    // (n*K + kk[n][p]) * NK: element offset of the G row of each kept candidate
     float uv[N][N][16];      // uv[a][m][p] = G[(m,old_m), (a, kk_a[p])]
-    float2 sel[32];          // result of the current selection: (key, flat), ascending
-#if MCQ_MERGE_PAIR
-    float2 sel2[32];         // result of the second of two interleaved merge selections
-#endif
-    float kd2[NG2][16];      // kept deltas / slot tuples after the first merge
-    unsigned kt2[NG2][16];
     float kd3[NG3][32];      // ... after the second merge
     unsigned kt3[NG3][32];
     int old[N];              // indexes at the start of the pass (and its result)
@@ -1171,6 +1179,10 @@ int launch2t(const float *P, const float *G, int64_t B, int iters, const int32_t
     const size_t smem = sizeof(WarpMem2<N>) * wpc;
     auto kern = search2_kernel<N>;
     MCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#ifdef MCQ_S2_CARVEOUT
+    // percent of the 228 KB the SM may give to shared memory; the rest of the 256 KB is L1
+    MCQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, MCQ_S2_CARVEOUT));
+#endif
     int per_sm = 1;
     MCQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
     if (per_sm < 1) per_sm = 1;
