@@ -1,5 +1,5 @@
 // search2.cu -- second version of the refinement search (all passes of Quantizer._refine_indexes,
-// quantization.py:308-547, for a batch of frames in ONE launch) for codebook_size 256 and 2, 4 or 8 codebooks: the
+// quantization.py:308-547, for a batch of frames in ONE launch) for codebook_size 256 and 2, 4, 8 or 16 codebooks: the
 // inference configurations.  Same tables (P = x Cs^T per frame, G = Cs Cs^T per parameter version), same
 // arithmetic contract and tie rules as search.cu / oracle/mcq_gram_model.c -- the tests compare both kernels with
 // that model bit for bit -- but organised around what the first version's profile showed (profiles/r01_ncu_summary.md:
@@ -8,12 +8,15 @@
 //   * one warp per frame; a lane owns 8 CONSECUTIVE candidates (flat = lane*8 + t), so level-1 rows are float4 loads
 //     and "lowest lane among equals" is "lowest flat index among equals" (the contract's tie rule);
 //   * sorted top-R: each lane rank-sorts its 8 keys into its own shared-memory column, then R steps of
-//     redux.sync.min.f32 (CREDUX) + ballot pop the global minimum from the column heads;
+//     redux.sync.min.f32 (CREDUX) pop the global minimum from the column heads -- one reduction per pop (predicated
+//     PTX, pop_step), with an exact two-reduction loop as the fallback when two lanes hold bit-equal keys;
 //   * every u/v term of a difference D_ab(p,q) = ((G[ap,bq] - G[ap,b_old]) - G[a_old,bq]) + G[a_old,b_old] comes from one
 //     cached gather uv[a][m][p] = G[(m,old_m),(a,kk_a[p])] (G is bitwise symmetric);
 //   * merge of single codebooks (16x16): one G gather per joint candidate; merge of codebook pairs (16x16): four;
 //     merge of codebook quads (32x32): 16x16 tables T_ab per codebook pair, folded per candidate row into
-//     E_b[i][q] = sum_a T_ab[i_a][q] -- exactly the contract's inner sum -- then dot(i,j) = sum_b E_b[i][j_b].
+//     E_b[i][q] = sum_a T_ab[i_a][q] -- exactly the contract's inner sum -- then dot(i,j) = sum_b E_b[i][j_b]; the
+//     tables hold only the slots the surviving candidates still use (columns compacted, unused rows skipped).
+// Round-2 measurements, ablations and the variants that lost are in profiles/r02_search.md.
 #include <stdlib.h>
 #include <string.h>
 
