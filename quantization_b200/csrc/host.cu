@@ -114,8 +114,7 @@ HostWs host_ws_layout(int64_t Bc, int D, int N, int K, int x_dtype, int codes_dt
 }
 
 constexpr int64_t HOST_CHUNK = 148 * 128 * 4;  // 75,776 frames: one chunk of mcq_encode (four waves of GEMM tiles)
-constexpr int64_t HOST_FIRST = 148 * 128;      // ramp: chunks of 1, 2, then 4 waves -- the first copy is the only one
-                                               // nothing hides, and each later copy must fit under the compute before it
+constexpr int64_t HOST_FIRST = 148 * 128;      // one wave: the unit of the chunk-size ramp (see the loop)
 
 }  // namespace
 
@@ -235,8 +234,18 @@ extern "C" int mcq_encode_host_ws(const void *x_host, int x_dtype, int64_t B, in
     int64_t chunk = 0;
     for (int64_t b0 = 0, nb = 0; b0 < B; b0 += nb, ++chunk) {
         const int k = (int)(chunk & 1);
-        nb = B - b0 < Bc ? B - b0 : Bc;
-        if (chunk < 2 && nb > (HOST_FIRST << chunk)) nb = HOST_FIRST << chunk;
+        // chunk sizes ramp 1, 2, 4, ... 4, 2, 1 waves: the first copy and the last compute are the only stages nothing
+        // overlaps (the last matters when the host link is the bottleneck: 8 ranks on one host)
+        const int64_t left = B - b0, w = HOST_FIRST;
+        nb = left < Bc ? left : Bc;
+        if (chunk < 2 && nb > (w << chunk)) nb = w << chunk;
+        if (left > w && left <= 3 * w) {
+            if (nb > left - w) nb = left - w;                            // ... then one last wave
+        } else if (left > 3 * w && left <= 7 * w) {
+            if (nb > left - 3 * w) nb = left - 3 * w;                    // ... then 2 + 1 waves
+        }
+        nb = (nb + 127) / 128 * 128;  // whole GEMM tiles, except at the very end
+        if (nb > left) nb = left;
         if (chunk >= 2) MCQ_CUDA(cudaStreamWaitEvent(r.s_in, r.ev_cmp[k], 0));  // x buffer k was read by chunk - 2
         MCQ_CUDA(cudaMemcpyAsync(base + L.off_x[k], (const char *)x_host + (size_t)b0 * D * xelt, (size_t)nb * D * xelt,
                                  cudaMemcpyHostToDevice, r.s_in));
