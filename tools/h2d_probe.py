@@ -21,11 +21,14 @@ dst = torch.empty(NB, dtype=torch.uint8, device=dev)
 rt = ctypes.CDLL("libcudart.so.12")
 
 
-def timed(src_ptr, label):
+def timed(src_ptr, label, piece=NB):
     def copy():
-        rc = rt.cudaMemcpyAsync(ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(src_ptr), ctypes.c_size_t(NB), 1,
-                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-        assert rc == 0, rc
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for off in range(0, NB, piece):
+            n = min(piece, NB - off)
+            rc = rt.cudaMemcpyAsync(ctypes.c_void_p(dst.data_ptr() + off), ctypes.c_void_p(src_ptr + off),
+                                    ctypes.c_size_t(n), 1, st)
+            assert rc == 0, rc
     copy()
     if world > 1:
         dist.barrier()
@@ -48,6 +51,8 @@ def timed(src_ptr, label):
 pinned = torch.empty(NB, dtype=torch.uint8).pin_memory()
 pinned.fill_(1)
 timed(pinned.data_ptr(), "pinned (torch pin_memory)")
+for mb in (256, 64, 16, 4):
+    timed(pinned.data_ptr(), f"pinned, in pieces of {mb} MiB", mb << 20)
 del pinned
 p = ctypes.c_void_p()
 rc = rt.cudaHostAlloc(ctypes.byref(p), ctypes.c_size_t(NB), 4)  # cudaHostAllocWriteCombined
