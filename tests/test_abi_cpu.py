@@ -47,6 +47,15 @@ def test_sizes_and_shape_validation():
     assert L.mcq_encode(None, 0, 16, 512, 8, 256, None, 5, None, 0, None, 0, None) == -1
     assert L.mcq_encode(None, 0, 0, 512, 8, 256, None, 5, None, 0, None, 0, None) == 0  # empty batch is a no-op
     assert L.mcq_decode(None, 0, 4, 3, 8, 256, 512, None, None, 0, None) == -1  # 3 columns do not divide 8
+    # host-buffer encode, re-entrant form: staging size = two frame buffers + two code buffers + one encode workspace
+    # of the largest chunk (75,776 frames), monotone in the batch up to that chunk; bad arguments rejected up front
+    big = L.mcq_encode_host_ws_bytes(1 << 20, 512, 8, 256, _lib.F32, _lib.U8)
+    small = L.mcq_encode_host_ws_bytes(1000, 512, 8, 256, _lib.F32, _lib.U8)
+    assert big == L.mcq_encode_host_ws_bytes(1 << 22, 512, 8, 256, _lib.F32, _lib.U8) > small > 0
+    assert big >= 2 * 75776 * 512 * 4 + L.mcq_workspace_bytes(75776, 512, 8, 256)
+    assert L.mcq_encode_host_ws_bytes(1000, 512, 3, 256, _lib.F32, _lib.U8) == 0
+    assert L.mcq_encode_host_ws(None, 0, 16, 512, 8, 256, None, 5, None, 0, None, 0, None) == -1
+    assert L.mcq_encode_host_ws(None, 0, 0, 512, 8, 256, None, 5, None, 0, None, 0, None) == 0
 
 
 def test_quantizer_surface_and_init_rng_order():
