@@ -150,6 +150,7 @@ __device__ __forceinline__ float2 list_sentinel() { return make_float2(__int_as_
 // frames, duplicated codebook rows); the profile of the two-reduction loop had 39 % of the kernel's stall samples.
 template <class Mem, int R>
 __device__ __noinline__ void pops_exact(Mem &s, float2 (*lists)[32], float2 *sel, int lane) {
+    __syncwarp();  // sel[] holds the fast path's stores of other lanes: order them before this loop's
     const float2 *col = &lists[0][lane];
     float2 head = col[0], nxt = col[32];
 #pragma unroll 1
@@ -175,6 +176,15 @@ __device__ __noinline__ void pops_exact(Mem &s, float2 (*lists)[32], float2 *sel
 //   sel[r], takes its prefetched successor as the new head and prefetches the entry after that.
 //   hk/hf: head (key, flat), nk/nf: its successor, a: shared address of the head's row in this lane's column (rows are
 //   256 bytes apart), sel_a: shared address of sel[first step of the group], U: step within the group.
+// When two lanes hold bit-equal minima both pop in the same step and both store to sel[r]: a write-after-write that
+// compute-sanitizer's racecheck reports.  It is benign -- the popped count is then not R and pops_exact redoes the whole
+// selection, overwriting sel -- and -DMCQ_POP_RACEFREE=1 proves it is the only one: the store is then issued only by a
+// lane that pops alone (one vote + three integer instructions more per pop: 4.76 vs 4.50 ms per launch), racecheck
+// reports no error and the
+// results are bit-identical (profiles/r02_racecheck_search.log).
+#ifndef MCQ_POP_RACEFREE
+#define MCQ_POP_RACEFREE 0
+#endif
 template <int U>
 __device__ __forceinline__ void pop_step(float &hk, float &hf, float &nk, float &nf, unsigned &a, unsigned sel_a) {
     asm volatile(
@@ -183,7 +193,17 @@ __device__ __forceinline__ void pop_step(float &hk, float &hf, float &nk, float 
         ".reg .f32 m;\n\t"
         "redux.sync.min.f32 m, %0, 0xffffffff;\n\t"
         "setp.eq.f32 p, %0, m;\n\t"
+#if MCQ_POP_RACEFREE
+        ".reg .pred s;\n\t"
+        ".reg .b32 b, c;\n\t"
+        "vote.sync.ballot.b32 b, p, 0xffffffff;\n\t"
+        "add.u32 c, b, -1;\n\t"
+        "and.b32 c, c, b;\n\t"
+        "setp.eq.and.u32 s, c, 0, p;\n\t"
+        "@s st.shared.v2.f32 [%5+%6], {%0, %1};\n\t"
+#else
         "@p st.shared.v2.f32 [%5+%6], {%0, %1};\n\t"
+#endif
         "@p mov.f32 %0, %2;\n\t"
         "@p mov.f32 %1, %3;\n\t"
         "@p ld.shared.v2.f32 {%2, %3}, [%4+512];\n\t"

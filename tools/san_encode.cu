@@ -111,6 +111,26 @@ int main(int argc, char **argv) {
             CK(mcq_gemm_nt(d_out, D, cs, D, B, nn, D, d_nt, nn, 1, d_wnt, wnt, nullptr));
         }
     }
+    {  // host-buffer encode, re-entrant form: pinned host frames / codes, caller-owned staging, a non-default stream
+        const int hdt = xdt == 0 ? MCQ_F32 : MCQ_F16;
+        const size_t hb = mcq_encode_host_ws_bytes(B, D, N, K, hdt, MCQ_U8);
+        void *staging, *hx, *hc;
+        cudaStream_t hs;
+        cudaMalloc(&staging, hb);
+        cudaMallocHost(&hx, x.size() * (xdt == 0 ? 4 : 2));
+        cudaMallocHost(&hc, (size_t)B * cols);
+        cudaMemcpy(hx, d_x, x.size() * (xdt == 0 ? 4 : 2), cudaMemcpyDeviceToHost);
+        cudaStreamCreate(&hs);
+        CK(mcq_encode_host_ws(hx, hdt, B, D, N, K, blob, 3, hc, MCQ_U8, staging, hb, hs));
+        CK(mcq_encode_host_ws(hx, hdt, B, D, N, K, blob, 3, hc, MCQ_U8, staging, hb / 2 + 4096, hs));  // smaller chunks
+        cudaStreamSynchronize(hs);
+        std::vector<unsigned char> dc((size_t)B * cols);
+        cudaMemcpy(dc.data(), d_codes, dc.size(), cudaMemcpyDeviceToHost);
+        long diff = 0;
+        for (size_t i = 0; i < dc.size(); ++i) diff += dc[i] != ((unsigned char *)hc)[i];
+        printf("encode_host_ws vs encode: %ld differing bytes\n", diff);
+        if (diff) return 1;
+    }
     cudaError_t e = cudaDeviceSynchronize();
     std::vector<unsigned char> codes((size_t)B * cols);
     cudaMemcpy(codes.data(), d_codes, codes.size(), cudaMemcpyDeviceToHost);
