@@ -17,6 +17,7 @@
 //     E_b[i][q] = sum_a T_ab[i_a][q] -- exactly the contract's inner sum -- then dot(i,j) = sum_b E_b[i][j_b]; the
 //     tables hold only the slots the surviving candidates still use (columns compacted, unused rows skipped).
 // Round-2 measurements, ablations and the variants that lost are in profiles/r02_search.md.
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -53,6 +54,9 @@ constexpr int POP_UNROLL = MCQ_POP_UNROLL;
 #endif
 #ifndef MCQ_S2_MINB4
 #define MCQ_S2_MINB4 1
+#endif
+#ifndef MCQ_S16_PAIR
+#define MCQ_S16_PAIR 1  // interleave the level-1 selections of two codebooks in the 16-codebook kernel as well
 #endif
 #ifndef MCQ_S16_WPC
 #define MCQ_S16_WPC 8
@@ -132,6 +136,22 @@ struct alignas(16) WarpMem2 {
     unsigned rowoff[N];      // (m*K + old[m]) * NK: element offset of the G row of each current entry
     unsigned used[8];        // quad merge: which level-1 slots of each codebook the 32+32 candidates still use
 };
+
+// Scratch of the second of two interleaved level-1 selections (level1<.., PAIR>): its column lists live in the (not yet
+// gathered) uv region, its result in the (not yet written) kd2 region.
+template <int N>
+__device__ __forceinline__ float2 (*pair_lists2(WarpMem2<N> &s))[32] {
+    static_assert(sizeof(s.uv) >= 10 * 32 * sizeof(float2), "pair memory");
+    return reinterpret_cast<float2(*)[32]>(&s.uv[0][0][0]);
+}
+template <int N>
+__device__ __forceinline__ float2 *pair_sel2(WarpMem2<N> &s) {
+    static_assert(sizeof(s.kd2) >= 16 * sizeof(float2), "pair memory");
+    return reinterpret_cast<float2 *>(&s.kd2[0][0]);
+}
+struct WarpMem16;
+__device__ __forceinline__ float2 (*pair_lists2(WarpMem16 &s))[32];
+__device__ __forceinline__ float2 *pair_sel2(WarpMem16 &s);
 
 // Sentinel below the 8 entries of a lane's column: NaN.  redux.sync.min.f32 ignores NaN inputs (the result is NaN only
 // when every lane's head is the sentinel) and `head == min` is false for it, so an exhausted lane never pops again and
@@ -384,9 +404,8 @@ __device__ __forceinline__ void level1(Mem &s, const float *__restrict__ Pb, con
 #pragma unroll
     for (int t = 0; t < 8; ++t) flat[t] = (t < 4 ? 0 : 128 - 4) + lane * 4 + t;
     if constexpr (PAIR) {
-        static_assert(sizeof(s.uv) >= 10 * 32 * sizeof(float2) && sizeof(s.kd2) >= 16 * sizeof(float2), "pair memory");
-        float2(*lists2)[32] = reinterpret_cast<float2(*)[32]>(&s.uv[0][0][0]);
-        float2 *sel2 = reinterpret_cast<float2 *>(&s.kd2[0][0]);
+        float2(*lists2)[32] = pair_lists2(s);  // scratch of the second chain: regions that are dead during level 1
+        float2 *sel2 = pair_sel2(s);
 #pragma unroll 1
         for (int n = 0; n < N; n += 2) {
             float keyA[8], keyB[8];
@@ -802,6 +821,15 @@ struct alignas(16) WarpMem16 {
     unsigned used[16];
 };
 
+// second level-1 chain of the 16-codebook kernel: lists in kd2 .. kt4 (exactly 10 rows of 32 float2, all written only by
+// the merges), result in the u-term buffer
+__device__ __forceinline__ float2 (*pair_lists2(WarpMem16 &s))[32] {
+    static_assert(offsetof(WarpMem16, kt4) + sizeof(WarpMem16::kt4) - offsetof(WarpMem16, kd2) == 10 * 32 * sizeof(float2),
+                  "pair memory");
+    return reinterpret_cast<float2(*)[32]>(&s.kd2[0][0]);
+}
+__device__ __forceinline__ float2 *pair_sel2(WarpMem16 &s) { return reinterpret_cast<float2 *>(&s.ul[0][0]); }
+
 // ul/vl of the NA x NB codebook pairs (a_base + la, b_base + lb), pair index c = la * NB + lb.
 // Lanes 0..15 fetch u (slot p = lane), lanes 16..31 fetch v (slot q = lane - 16).
 template <int NA, int NB>
@@ -1076,7 +1104,7 @@ __device__ __forceinline__ void merge8_final_16(WarpMem16 &s, const float *__res
 __device__ __forceinline__ void refine_pass16(WarpMem16 &s, const float *__restrict__ Pb, const float *__restrict__ G, int lane) {
     if (lane < 16) s.rowoff[lane] = (unsigned)(lane * K2 + s.old[lane]) * (unsigned)(16 * K2);
     __syncwarp();
-    level1<16, WarpMem16, false>(s, Pb, G, lane);
+    level1<16, WarpMem16, MCQ_S16_PAIR != 0>(s, Pb, G, lane);
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) merge1_16(s, G, g, lane);
 #pragma unroll 1
