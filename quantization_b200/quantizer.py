@@ -29,6 +29,7 @@ def _is_power_of_two(n: int) -> bool:
 # smallest codebook_size that takes the fused classifier-loss kernels (below it: the PyTorch formulation)
 _FUSED_LOSS_MIN_K = int(os.environ.get("MCQ_FUSED_LOSS_MIN_K", "16"))
 _CHECK_INDEXES = os.environ.get("MCQ_CHECK_INDEXES", "0") == "1"
+_SLAB_MIN_FRAMES = 16384  # csrc/decode.cu SLAB_MIN_FRAMES: from here on byte codes take the slab decode kernel
 # largest shapes the search kernels cover (csrc/api.cu check_shape); the reference itself has no such limit
 MAX_CODEBOOK_SIZE = 256
 MAX_NUM_CODEBOOKS = 64
@@ -384,6 +385,10 @@ class Quantizer(nn.Module):
         else:
             L = _lib.lib()
             blob = self._prepared()
+            if (idx.dtype != torch.uint8 and ncols == N and N in (4, 8) and D % 32 == 0 and B >= _SLAB_MIN_FRAMES):
+                # large batches of int32 / int64 indexes: one narrowing pass (out-of-range indexes become entry 0, as
+                # the kernels treat them) buys the shared-memory slab kernel, which takes byte codes
+                idx = torch.where((idx < 0) | (idx >= K), torch.zeros_like(idx), idx).to(torch.uint8)
             out = torch.empty(B, D, dtype=torch.float32, device=idx.device)
             if B > 0:
                 with torch.cuda.device(idx.device):

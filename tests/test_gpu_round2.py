@@ -340,16 +340,28 @@ def test_decode_slab_matches_row_gather(N, K, D, B):
     cd = codes.to(DEV)
     c64 = cd.to(torch.int64)
     idx64 = torch.where(c64 >= K, torch.zeros_like(c64), c64).contiguous()
+    L = _lib.lib()
+    blob = q._prepared()
     with torch.no_grad():
         slab = q.decode(cd)
-        rows = q.decode(idx64)
+        narrowed = q.decode(idx64)  # large int64 batches are narrowed to bytes and take the slab kernel too
         cs = q.get_centers().cpu().numpy()
-    assert torch.equal(slab, rows)
+    rows = torch.empty(B, D, dtype=torch.float32, device=DEV)  # int64 codes through the C ABI: the row-gather kernel
+    _lib.check(L.mcq_decode(idx64.data_ptr(), _lib.I64, B, N, N, K, D, blob.data_ptr(), rows.data_ptr(), _lib.F32,
+                            _lib.stream_ptr(DEV)), "mcq_decode")
+    torch.cuda.synchronize()
+    assert torch.equal(slab, rows) and torch.equal(narrowed, rows)
+    bad = c64.clone()
+    bad[7, 0] = K + 5
+    bad[9, N - 1] = -3
+    with torch.no_grad():  # out-of-range indexes decode as entry 0 on either path
+        fixed = c64.clone()
+        fixed[7, 0] = 0
+        fixed[9, N - 1] = 0
+        assert torch.equal(q.decode(bad), q.decode(torch.where(fixed >= K, torch.zeros_like(fixed), fixed)))
     ref = oracle.decode(idx64[:1024].cpu().numpy(), cs)
     assert np.array_equal(slab[:1024].cpu().numpy(), ref)
     # half / bfloat16 outputs through the C ABI (Quantizer.decode returns fp32)
-    L = _lib.lib()
-    blob = q._prepared()
     for dt, code in ((torch.float16, _lib.F16), (torch.bfloat16, _lib.BF16)):
         a = torch.empty(B, D, dtype=dt, device=DEV)
         b = torch.empty(B, D, dtype=dt, device=DEV)
