@@ -122,6 +122,20 @@ int mcq_class_loss_backward(const float *xw, int64_t num_frames, int dim, int nu
                             const float *g_prob_sum, float *grad_logits, float *part_gx, void *stream);
 
 /*
+ * The two small reductions left of Quantizer.compute_loss / its backward once the kernels above have run:
+ * mcq_index_counts: counts (N*K floats) = per-codebook histogram of the chosen entries, the `counts.mean(dim=0) * B` of
+ *   quantization.py:227-231 without the (B, N, K) one-hot tensor (idx (B, N) int64; entries outside [0, K) are not
+ *   counted; scratch: N*K uint32; N*K <= 12,288).  Integer counting: the result is independent of the order.
+ * mcq_column_sums: out[c] = sum_r x[r][c] for a contiguous (rows, cols) fp32 matrix -- the bias gradient
+ *   grad_logits.sum(0) autograd forms for nn.Linear (backward of quantization.py:279); cols a multiple of 4; partials:
+ *   mcq_column_sum_partials(cols) floats; fixed summation order (reproducible).
+ */
+int mcq_index_counts(const int64_t *idx, int64_t num_frames, int num_codebooks, int codebook_size, float *counts,
+                     void *scratch, void *stream);
+int mcq_column_sum_partials(int cols);
+int mcq_column_sums(const float *x, int64_t rows, int cols, float *out, float *partials, void *stream);
+
+/*
  * Reconstruction term of Quantizer.compute_loss (quantization.py:209-216) without its (B, dim) intermediates.
  * Forward: sums[0] = sum_{b,d} (x_hat - x)^2 with x_hat = decode(idx) (scaled centers summed n = 0..N-1), sums[1] =
  * sum_{b,d} (x - mean)^2 (mean (dim) fp32 = Quantizer.get_data_mean()); x (B, dim) fp32 / fp16 / bf16, idx (B, N) int64;

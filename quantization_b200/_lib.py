@@ -50,6 +50,9 @@ def lib():
         "mcq_class_loss_forward": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
         "mcq_class_loss_partials": (i32, []),
         "mcq_class_loss_backward": (i32, [vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+        "mcq_index_counts": (i32, [vp, i64, i32, i32, vp, vp, vp]),
+        "mcq_column_sum_partials": (i32, [i32]),
+        "mcq_column_sums": (i32, [vp, i64, i32, vp, vp, vp]),
         "mcq_prepared_scaled_centers": (vp, [vp, i32, i32, i32]),
         "mcq_prepared_gram": (vp, [vp, i32, i32, i32]),
         "mcq_xct": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, vp, sz, vp]),
@@ -83,6 +86,7 @@ def lib():
 EXPORTS = ["mcq_version", "mcq_last_error", "mcq_packed_cols", "mcq_prepared_bytes", "mcq_workspace_bytes",
            "mcq_prepare", "mcq_encode", "mcq_refine", "mcq_decode", "mcq_decode_centers", "mcq_decode_backward",
            "mcq_class_loss_forward", "mcq_class_loss_backward", "mcq_class_loss_partials",
+           "mcq_index_counts", "mcq_column_sum_partials", "mcq_column_sums",
            "mcq_prepared_scaled_centers", "mcq_prepared_gram", "mcq_xct", "mcq_search", "mcq_encode_host",
            "mcq_encode_host_ws_bytes", "mcq_encode_host_ws",
            "mcq_recon_loss_partials", "mcq_recon_loss_forward", "mcq_recon_loss_backward",
@@ -161,6 +165,31 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(a.device):
         check(L.mcq_gemm_tn(a.data_ptr(), a.stride(0), b.data_ptr(), x_dtype_code(b), b.stride(0), R, C1, C2,
                             out.data_ptr(), ws.data_ptr(), nbytes, stream_ptr(a.device)), "mcq_gemm_tn")
+    return out
+
+
+def index_counts(idx: torch.Tensor, N: int, K: int) -> torch.Tensor:
+    """(N, K) float32 histogram of the int64 indexes (B, N) per codebook (include/mcq.h: mcq_index_counts)."""
+    L = lib()
+    assert idx.dtype == torch.int64 and idx.is_contiguous() and idx.shape[1] == N
+    counts = torch.empty(N, K, dtype=torch.float32, device=idx.device)
+    scratch = torch.empty(N * K, dtype=torch.int32, device=idx.device)
+    with torch.cuda.device(idx.device):
+        check(L.mcq_index_counts(idx.data_ptr(), idx.shape[0], N, K, counts.data_ptr(), scratch.data_ptr(),
+                                 stream_ptr(idx.device)), "mcq_index_counts")
+    return counts
+
+
+def column_sums(x: torch.Tensor) -> torch.Tensor:
+    """x.sum(0) of a contiguous fp32 (R, C) matrix, C a multiple of 4, in a fixed order (mcq_column_sums)."""
+    L = lib()
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.ndim == 2 and x.shape[1] % 4 == 0
+    R, C = x.shape
+    out = torch.empty(C, dtype=torch.float32, device=x.device)
+    part = torch.empty(L.mcq_column_sum_partials(C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(L.mcq_column_sums(x.data_ptr(), R, C, out.data_ptr(), part.data_ptr(), stream_ptr(x.device)),
+              "mcq_column_sums")
     return out
 
 

@@ -510,6 +510,35 @@ int mcq_class_loss_backward(const float *xw, int64_t B, int D, int N, int K, con
                                       g_logprob_sum, g_prob_sum, grad_logits, part_gx, (cudaStream_t)stream));
 }
 
+int mcq_index_counts(const int64_t *idx, int64_t B, int N, int K, float *counts, void *scratch, void *stream) {
+    if (B < 0 || N <= 0 || K <= 0) {
+        set_error("mcq_index_counts: bad shape");
+        return MCQ_EINVAL;
+    }
+    if (!counts || !scratch || (B > 0 && !idx)) {
+        set_error("mcq_index_counts: null pointer");
+        return MCQ_EINVAL;
+    }
+    return PROF(MCQ_PROF_OTHER, (cudaStream_t)stream,
+                launch_index_counts(idx, B, N, K, counts, (unsigned *)scratch, (cudaStream_t)stream));
+}
+
+int mcq_column_sum_partials(int cols) { return cols > 0 ? column_sum_partials(cols) : 0; }
+
+int mcq_column_sums(const float *x, int64_t rows, int cols, float *out, float *partials, void *stream) {
+    if (rows <= 0 || cols <= 0 || (cols & 3) || ((uintptr_t)x & 15)) {
+        set_error("mcq_column_sums: rows=%lld cols=%d (cols must be a multiple of 4, x 16-byte aligned)", (long long)rows,
+                  cols);
+        return MCQ_EINVAL;
+    }
+    if (!x || !out || !partials) {
+        set_error("mcq_column_sums: null pointer");
+        return MCQ_EINVAL;
+    }
+    return PROF(MCQ_PROF_OTHER, (cudaStream_t)stream,
+                launch_column_sums(x, rows, cols, out, partials, (cudaStream_t)stream));
+}
+
 int mcq_xct(const void *x, int x_dtype, int64_t B, int D, int N, int K, const void *prepared, float *P, void *workspace,
             size_t workspace_bytes, void *stream) {
     int rc = check_shape(N, K, D);

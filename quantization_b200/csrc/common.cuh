@@ -132,6 +132,12 @@ int class_loss_bwd_partials();
 int launch_class_loss_bwd(const float *xw, const float *bias, const int64_t *idx, int64_t B, int N, int K,
                           const float *g_lp, const float *g_prob, float *grad_logits, float *part_gx, cudaStream_t st);
 
+// counts (N*K floats) = histogram of idx (B, N) per codebook; scratch: N*K uint32 (N*K <= 12,288)
+int launch_index_counts(const int64_t *idx, int64_t B, int N, int K, float *counts, unsigned *scratch, cudaStream_t st);
+// out[c] = sum_r X[r][c] for a contiguous (R, C) fp32 matrix, C a multiple of 4; part: column_sum_partials(C) floats
+int column_sum_partials(int C);
+int launch_column_sums(const float *X, int64_t R, int C, float *out, float *part, cudaStream_t st);
+
 bool use_tensor_core_gemm();
 
 }  // namespace mcq

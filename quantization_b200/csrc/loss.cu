@@ -336,6 +336,88 @@ __global__ void __launch_bounds__(256) class_loss_bwd_small_kernel(const float *
         default: CALL(16, 1); break; /* K <= 16 */ \
     }
 
+// ---- histogram of the chosen entries (quantization.py:227-231: the per-codebook counts behind index_entropy_loss).
+// The reference scatters ones into a (B, N, K) tensor and averages it; a scatter_add of 65,536 x 8 ones into 128 bins
+// (trainer phase 1) is 92 us of contended global atomics.  Here every CTA counts its frames in shared memory (integer
+// atomics) and adds its bins to the global integer histogram once; a second tiny kernel converts to float.  Counts are
+// integers, so the result does not depend on the order of the additions.
+__global__ void __launch_bounds__(256) index_counts_kernel(const int64_t *__restrict__ idx, int64_t B, int N, int K,
+                                                           unsigned *__restrict__ counts) {
+    extern __shared__ unsigned hist[];
+    const int NK = N * K;
+    for (int i = threadIdx.x; i < NK; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int64_t total = B * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i % N);
+        const int64_t k = idx[i];
+        if (k >= 0 && k < K) atomicAdd(&hist[n * K + (int)k], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NK; i += blockDim.x) {
+        const unsigned v = hist[i];
+        if (v) atomicAdd(&counts[i], v);
+    }
+}
+
+__global__ void counts_to_float_kernel(const unsigned *__restrict__ counts, int n, float *__restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = (float)counts[i];
+}
+
+// ---- column sums of a tall matrix: out[c] = sum_r X[r][c] (the bias gradient grad_logits.sum(0): 65,536 x 128..1024).
+// Stage 1: CTA j sums rows j, j + G, j + 2G, ... (thread = column group of 4, fixed order) into part[j][c]; stage 2 adds
+// the G partial rows in ascending j: reproducible, no atomics.
+constexpr int COLSUM_PARTS = 148 * 4;
+
+__global__ void __launch_bounds__(256) colsum_part_kernel(const float *__restrict__ X, int64_t R, int C,
+                                                          float *__restrict__ part) {
+    const int C4 = C >> 2;
+    // thread -> (column group g, row lane rl): blockDim.x = 256 threads cover min(C4, 256) groups x the rest as row lanes
+    const int groups = C4 < 256 ? C4 : 256;
+    const int rlanes = 256 / groups;
+    const int g0 = threadIdx.x % groups, rl = threadIdx.x / groups;
+    __shared__ float4 red[256];
+    for (int base = 0; base < C4; base += groups) {  // uniform trip count: the loop holds barriers
+        const int g = base + g0;
+        const bool on = g < C4 && rl < rlanes;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on)
+            for (int64_t r = (int64_t)blockIdx.x * rlanes + rl; r < R; r += (int64_t)gridDim.x * rlanes) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(X + (size_t)r * C) + g);
+                acc.x += v.x;
+                acc.y += v.y;
+                acc.z += v.z;
+                acc.w += v.w;
+            }
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        if (on && rl == 0) {
+            for (int q = 1; q < rlanes; ++q) {  // fixed order over the row lanes
+                const float4 v = red[q * groups + g0];
+                acc.x += v.x;
+                acc.y += v.y;
+                acc.z += v.z;
+                acc.w += v.w;
+            }
+            reinterpret_cast<float4 *>(part + (size_t)blockIdx.x * C)[g] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// a warp per column: lane l adds partial rows l, l + 32, ... in ascending order, then a fixed shuffle tree
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float *__restrict__ part, int parts, int C,
+                                                            float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    float a = 0.0f;
+    for (int j = lane; j < parts; j += 32) a += part[(size_t)j * C + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) out[c] = a;
+}
+
 }  // namespace
 
 // number of frame streams (and so of partial rows) the forward kernel uses for a batch of B frames
@@ -410,6 +492,39 @@ int launch_class_loss_bwd(const float *xw, const float *bias, const int64_t *idx
     MCQ_LOSS_DISPATCH(K, MCQ_BWD)
 #undef MCQ_BWD
     MCQ_LAUNCH_CHECK("class_loss_bwd_kernel");
+    return MCQ_OK;
+}
+
+}  // namespace mcq
+
+namespace mcq {
+
+int launch_index_counts(const int64_t *idx, int64_t B, int N, int K, float *counts, unsigned *scratch, cudaStream_t st) {
+    const int NK = N * K;
+    if ((size_t)NK * sizeof(unsigned) > 48 * 1024) {
+        set_error("index counts: %d bins do not fit the shared-memory histogram", NK);
+        return MCQ_EUNSUPPORTED;
+    }
+    MCQ_CUDA(cudaMemsetAsync(scratch, 0, sizeof(unsigned) * NK, st));
+    int64_t blocks = (B * N + 256 * 16 - 1) / (256 * 16);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks < 1) blocks = 1;
+    index_counts_kernel<<<(unsigned)blocks, 256, NK * sizeof(unsigned), st>>>(idx, B, N, K, scratch);
+    MCQ_LAUNCH_CHECK("index_counts_kernel");
+    counts_to_float_kernel<<<(NK + 255) / 256, 256, 0, st>>>(scratch, NK, counts);
+    MCQ_LAUNCH_CHECK("counts_to_float_kernel");
+    return MCQ_OK;
+}
+
+int column_sum_partials(int C) { return COLSUM_PARTS * C; }
+
+int launch_column_sums(const float *X, int64_t R, int C, float *out, float *part, cudaStream_t st) {
+    int parts = COLSUM_PARTS;
+    if (parts > R) parts = (int)(R > 0 ? R : 1);
+    colsum_part_kernel<<<parts, 256, 0, st>>>(X, R, C, part);
+    MCQ_LAUNCH_CHECK("colsum_part_kernel");
+    colsum_reduce_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, parts, C, out);
+    MCQ_LAUNCH_CHECK("colsum_reduce_kernel");
     return MCQ_OK;
 }
 

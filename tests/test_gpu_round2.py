@@ -426,3 +426,26 @@ def test_other_configs_against_oracle(name, D, N, K, B, dtype):
     codes = q.encode(x.to(DEV)).cpu()
     with torch.no_grad():
         assert torch.equal(q.decode(codes.to(DEV)), q.decode(torch.from_numpy(idx).to(DEV)))
+
+
+@pytest.mark.parametrize("B,N,K", [(65536, 8, 16), (70001, 4, 256), (300, 16, 256), (5, 2, 32), (4096, 32, 256)])
+def test_index_counts_and_column_sums(B, N, K):
+    """mcq_index_counts against a bincount, mcq_column_sums against a float64 column sum (and reproducible)."""
+    g = torch.Generator().manual_seed(B + N)
+    idx = torch.randint(0, K, (B, N), generator=g, dtype=torch.int64)
+    idx[0, 0] = -1  # entries outside [0, K) are not counted
+    idx[B - 1, N - 1] = K
+    want = torch.zeros(N, K)
+    for n in range(N):
+        col = idx[:, n]
+        col = col[(col >= 0) & (col < K)]
+        want[n] = torch.bincount(col, minlength=K).float()
+    got = _lib.index_counts(idx.to(DEV), N, K).cpu()
+    assert torch.equal(got, want)
+    x = torch.randn(B, N * K, generator=g).to(DEV)
+    s1 = _lib.column_sums(x)
+    s2 = _lib.column_sums(x)
+    assert torch.equal(s1, s2)
+    ref = x.double().sum(0)
+    scale = x.double().abs().sum(0)
+    assert float(((s1.double() - ref).abs() / scale).max()) < 1e-6
