@@ -359,18 +359,24 @@ def config_c1(dev):
 
 
 def _trainer_phase_times(tr, x, steps, warm):
-    """(ms per regular step, ms of one diagnostics step) of the trainer's current phase.  cur_iter is moved so that
-    the `steps` regular steps stay clear of the every-200-iterations diagnostics and one diagnostics step follows."""
+    """(ms per regular step, ms of one diagnostics step) of the trainer's current phase.  cur_iter is kept clear of the
+    every-200-iterations diagnostics during the regular steps (it is stepped over a multiple of 200); the diagnostics
+    step is run once untimed first -- its first evaluation in a phase pays one-time costs (new workspaces, lazily
+    loaded kernels) that a 20,001-step run pays once, not 50 times -- and then timed."""
     import torch
     base = tr.cur_iter - tr.cur_iter % 200
     tr.cur_iter = base + 1
     for _ in range(warm):
         tr.step(x)
+    tr.cur_iter = base + 400
+    tr.step(x)  # diagnostics warm-up
     tr.cur_iter = base + 201
     torch.cuda.synchronize()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
     for _ in range(steps):
+        if tr.cur_iter % 200 == 0:
+            tr.cur_iter += 1
         tr.step(x)
     e1.record()
     tr.cur_iter = base + 400
